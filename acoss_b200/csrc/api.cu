@@ -1,0 +1,513 @@
+// C-ABI entry points and host-side orchestration (see include/acoss_b200.h).
+//
+// Pipeline per acoss_score_pairs* call (all asynchronous on the context stream):
+//   K1 oti_kernel over all pairs -> pairs are processed in fixed-pitch chunks ("slots"):
+//   K2 (fast sweep path, exact fallback) -> bit-packed CRP per slot -> K3 DP -> scores[k].
+// Nothing here computes on the CPU: without a usable device every call fails with ACOSS_E_CUDA.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "k2_fast.cuh"
+
+static thread_local char g_err[512] = "";
+
+void acoss_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct acoss_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // resident track set
+    float *d_frames = nullptr;
+    bool own_frames = false;
+    int64_t *d_offsets = nullptr;
+    float *d_gchroma = nullptr;
+    int32_t n_tracks = 0;
+    int32_t max_frames = 0, min_frames = 0;
+    int64_t total_frames = 0;
+    int64_t ws_limit = (int64_t)24 << 30;
+    // grow-only scratch
+    Buf pairs, scores, oti, status, crp, rows, cols, thr_q, thr_r, rrot, aa, bb, D, halo, misc, fast, fbmap;
+    uint32_t *h_flag = nullptr;   // pinned
+    int64_t stats[8] = {0};
+    int pending_status_check = 0;
+    int64_t pending_pairs = 0;
+};
+
+static int ensure(Buf &b, size_t bytes) {
+    if (bytes <= b.cap) return ACOSS_OK;
+    if (b.p) CUDA_TRY(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        acoss_set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        return ACOSS_E_NOMEM;
+    }
+    b.cap = want;
+    return ACOSS_OK;
+}
+#define TRY(x)                         \
+    do {                               \
+        int _rc = (x);                 \
+        if (_rc != ACOSS_OK) return _rc; \
+    } while (0)
+
+extern "C" {
+
+void acoss_default_params(acoss_params *p) {
+    if (!p) return;
+    p->m = 9; p->tau = 1; p->kappa = 0.095f; p->oti = 1; p->noti = 12;
+    p->gamma_o = 0.5f; p->gamma_e = 0.5f; p->align = ACOSS_ALIGN_QMAX; p->integer_guard = 0;
+    p->crp_path = ACOSS_CRP_AUTO;
+}
+
+const char *acoss_last_error(void) { return g_err; }
+const char *acoss_version(void) { return "acoss_b200 0.1 (sm_100a)"; }
+int acoss_compiled_sm(void) { return 100; }
+
+int acoss_create(acoss_ctx **out, int device) {
+    if (!out) { acoss_set_error("ctx is NULL"); return ACOSS_E_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        acoss_set_error("no CUDA device available (%s); acoss_b200 has no CPU fallback",
+                        e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return ACOSS_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) { acoss_set_error("device %d out of range (%d devices)", device, ndev); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        acoss_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return ACOSS_E_CUDA;
+    }
+    acoss_ctx *c = new acoss_ctx();
+    c->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMallocHost((void **)&c->h_flag, 64));
+    *out = c;
+    return ACOSS_OK;
+}
+
+static void free_buf(Buf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+int acoss_destroy(acoss_ctx *c) {
+    if (!c) return ACOSS_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    Buf *bufs[] = {&c->pairs, &c->scores, &c->oti, &c->status, &c->crp, &c->rows, &c->cols, &c->thr_q, &c->thr_r,
+                   &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap};
+    for (Buf *b : bufs) free_buf(*b);
+    if (c->own_frames && c->d_frames) cudaFree(c->d_frames);
+    if (c->d_offsets) cudaFree(c->d_offsets);
+    if (c->d_gchroma) cudaFree(c->d_gchroma);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return ACOSS_OK;
+}
+
+int acoss_set_workspace_limit(acoss_ctx *c, int64_t bytes) {
+    if (!c || bytes < ((int64_t)64 << 20)) { acoss_set_error("workspace limit must be >= 64 MiB"); return ACOSS_E_INVALID; }
+    c->ws_limit = bytes;
+    return ACOSS_OK;
+}
+
+void *acoss_stream(acoss_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int acoss_set_tracks(acoss_ctx *c, const float *frames, const int64_t *offsets, int32_t n_tracks, int on_device) {
+    if (!c || !frames || !offsets || n_tracks <= 0) { acoss_set_error("set_tracks: bad arguments"); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int64_t mx = 0, mn = INT64_MAX;
+    for (int t = 0; t < n_tracks; ++t) {
+        const int64_t n = offsets[t + 1] - offsets[t];
+        if (n < 0 || offsets[0] != 0) { acoss_set_error("set_tracks: offsets must start at 0 and be non-decreasing"); return ACOSS_E_INVALID; }
+        mx = std::max(mx, n);
+        mn = std::min(mn, n);
+    }
+    if (mx > (1 << 20)) { acoss_set_error("set_tracks: track longer than 2^20 frames"); return ACOSS_E_INVALID; }
+    const int64_t total = offsets[n_tracks];
+    if (c->own_frames && c->d_frames) CUDA_TRY(cudaFree(c->d_frames));
+    c->d_frames = nullptr;
+    if (c->d_offsets) CUDA_TRY(cudaFree(c->d_offsets));
+    if (c->d_gchroma) CUDA_TRY(cudaFree(c->d_gchroma));
+    c->d_offsets = nullptr; c->d_gchroma = nullptr;
+    if (on_device) {
+        c->d_frames = const_cast<float *>(frames);
+        c->own_frames = false;
+    } else {
+        // +16 floats of zero padding so vector loads past the last frame stay in bounds
+        CUDA_TRY(cudaMalloc((void **)&c->d_frames, (size_t)(total * NBINS + 64) * sizeof(float)));
+        c->own_frames = true;
+        CUDA_TRY(cudaMemsetAsync(c->d_frames + total * NBINS, 0, 64 * sizeof(float), c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->d_frames, frames, (size_t)total * NBINS * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    CUDA_TRY(cudaMalloc((void **)&c->d_offsets, (size_t)(n_tracks + 1) * sizeof(int64_t)));
+    CUDA_TRY(cudaMalloc((void **)&c->d_gchroma, (size_t)n_tracks * NBINS * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(c->d_offsets, offsets, (size_t)(n_tracks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    c->n_tracks = n_tracks;
+    c->max_frames = (int32_t)mx;
+    c->min_frames = (int32_t)mn;
+    c->total_frames = total;
+    TRY(launch_global_chroma(c->d_frames, c->d_offsets, n_tracks, c->d_gchroma, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ACOSS_OK;
+}
+
+static TrackSet track_set(const acoss_ctx *c) {
+    TrackSet ts;
+    ts.frames = c->d_frames; ts.offsets = c->d_offsets; ts.gchroma = c->d_gchroma;
+    ts.n_tracks = c->n_tracks; ts.max_frames = c->max_frames;
+    return ts;
+}
+
+static int check_params(const acoss_ctx *c, const acoss_params *p) {
+    if (!c || !p) { acoss_set_error("NULL context or params"); return ACOSS_E_INVALID; }
+    if (!c->d_frames) { acoss_set_error("no tracks resident: call acoss_set_tracks first"); return ACOSS_E_INVALID; }
+    if (p->m < 1 || p->m > 64 || p->tau < 1 || p->tau > 64) { acoss_set_error("m and tau must be in 1..64"); return ACOSS_E_INVALID; }
+    if (!(p->kappa >= 0.f && p->kappa <= 1.f)) { acoss_set_error("kappa must be in [0,1]"); return ACOSS_E_INVALID; }
+    if (p->noti < 0 || p->noti > 64) { acoss_set_error("noti out of range"); return ACOSS_E_INVALID; }
+    if (p->align != ACOSS_ALIGN_QMAX) { acoss_set_error("align mode %d not implemented for the pair pipeline", p->align); return ACOSS_E_INVALID; }
+    const int incr = p->m * p->tau;
+    if (c->min_frames < incr + 2) {
+        acoss_set_error("a track has %d frames; essentia needs at least m*tau+2 = %d (F9)", c->min_frames, incr + 2);
+        return ACOSS_E_TOO_SHORT;
+    }
+    return ACOSS_OK;
+}
+
+__global__ void or_reduce_kernel(const uint32_t *__restrict__ status, int64_t n, uint32_t *__restrict__ out) {
+    uint32_t v = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v |= status[i];
+    v = __reduce_or_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicOr(out, v);
+}
+__global__ void count_bits_kernel(const uint32_t *__restrict__ status, int64_t n, uint32_t bit, unsigned long long *out) {
+    unsigned c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += (status[i] & bit) ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+struct DumpOut {
+    int32_t *oti = nullptr;
+    uint32_t *crp = nullptr;
+    float *thr_q = nullptr, *thr_r = nullptr;
+};
+
+// Core pipeline.  pairs_dev / scores_dev are device pointers.
+static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const acoss_params *p, float *scores_dev,
+                     DumpOut *dump) {
+    TRY(check_params(c, p));
+    if (K <= 0) return ACOSS_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const TrackSet ts = track_set(c);
+    const int incr = p->m * p->tau;
+    SlotGeom g;
+    g.max_rows = c->max_frames - incr;
+    g.max_cols = c->max_frames - incr;
+    g.words = (g.max_cols + 31) / 32 + 1;
+    g.crp_words = (int64_t)g.max_rows * g.words;
+    const int64_t ldd = ((int64_t)g.max_cols + 31) / 32 * 32;
+    const int64_t halo_pitch = g.max_rows;
+    memset(c->stats, 0, sizeof(c->stats));
+    int64_t launches = 0;
+
+    TRY(ensure(c->oti, (size_t)K * 4));
+    TRY(ensure(c->status, (size_t)K * 4 + 64));
+    TRY(ensure(c->misc, 256));
+    CUDA_TRY(cudaMemsetAsync(c->status.p, 0, (size_t)K * 4 + 64, st));
+    CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 256, st));
+    TRY(launch_oti(ts, pairs_dev, K, p->noti, p->oti, (int32_t *)c->oti.p, st));
+    ++launches;
+
+    const bool fast = (p->crp_path == ACOSS_CRP_AUTO) && k2_fast_supported(*p, g);
+    // bytes per slot
+    const size_t exact_slot = (size_t)g.max_rows * ldd * 4 + (size_t)c->max_frames * NBINS * 4 + (size_t)(g.max_rows + g.max_cols) * 4;
+    const size_t common_slot = (size_t)g.crp_words * 4 + (size_t)(g.max_rows + g.max_cols) * 4 + 8 + (size_t)2 * halo_pitch * 16;
+    const size_t fast_slot = fast ? k2_fast_slot_bytes(g) : 0;
+    const size_t per_slot = common_slot + (fast ? fast_slot : exact_slot);
+    int64_t slots = std::max<int64_t>(1, (int64_t)(c->ws_limit / (int64_t)per_slot));
+    slots = std::min<int64_t>(slots, std::min<int64_t>(K, 16384));
+    // exact-fallback slots available to the fast path (flagged pairs are re-run in small groups)
+    const int fb_slots = fast ? (int)std::max<int64_t>(1, std::min<int64_t>(16, ((int64_t)2 << 30) / (int64_t)exact_slot)) : 0;
+    const int64_t ex_slots = fast ? fb_slots : slots;
+
+    TRY(ensure(c->crp, (size_t)slots * g.crp_words * 4));
+    TRY(ensure(c->rows, (size_t)slots * 4));
+    TRY(ensure(c->cols, (size_t)slots * 4));
+    TRY(ensure(c->thr_q, (size_t)slots * g.max_rows * 4));
+    TRY(ensure(c->thr_r, (size_t)slots * g.max_cols * 4));
+    TRY(ensure(c->halo, (size_t)slots * 2 * halo_pitch * 16));
+    TRY(ensure(c->rrot, (size_t)ex_slots * c->max_frames * NBINS * 4));
+    TRY(ensure(c->aa, (size_t)ex_slots * g.max_rows * 4));
+    TRY(ensure(c->bb, (size_t)ex_slots * g.max_cols * 4));
+    TRY(ensure(c->D, (size_t)ex_slots * g.max_rows * ldd * 4));
+    if (fast) TRY(ensure(c->fast, (size_t)slots * fast_slot + 4096));
+    ExactScratch sc;
+    sc.rrot = (float *)c->rrot.p; sc.aa = (float *)c->aa.p; sc.bb = (float *)c->bb.p; sc.D = (float *)c->D.p;
+    sc.ldd = ldd; sc.slots = (int32_t)ex_slots;
+
+    uint32_t *status = (uint32_t *)c->status.p;
+    for (int64_t first = 0; first < K; first += slots) {
+        const int n = (int)std::min<int64_t>(slots, K - first);
+        TRY(launch_pair_geometry(ts, pairs_dev, first, n, incr, (int32_t *)c->rows.p, (int32_t *)c->cols.p, st));
+        ++launches;
+        if (fast) {
+            TRY(launch_k2_fast(ts, pairs_dev, (const int32_t *)c->oti.p, first, n, *p, g, c->fast.p, fast_slot,
+                               (uint32_t *)c->crp.p, (float *)c->thr_q.p, (float *)c->thr_r.p, status, st, &launches));
+            // exact fallback for pairs the fast path flagged: compact their slot ids, re-run in groups
+            TRY(ensure(c->fbmap, (size_t)slots * 4 + 64));
+            int nfb = 0;
+            TRY(k2_fast_collect_fallback(status, first, n, (int32_t *)c->fbmap.p, (int32_t *)((char *)c->misc.p + 128), &nfb, st));
+            if (nfb > 0) {
+                c->stats[1] += nfb;
+                for (int b0 = 0; b0 < nfb; b0 += fb_slots) {
+                    const int nb = std::min(fb_slots, nfb - b0);
+                    TRY(launch_k2_exact(ts, pairs_dev, (const int32_t *)c->oti.p, first, nb, *p, g, sc, (uint32_t *)c->crp.p,
+                                        (float *)c->thr_q.p, (float *)c->thr_r.p, status, (const int32_t *)c->fbmap.p + b0, st,
+                                        &launches));
+                }
+            }
+        } else {
+            TRY(launch_k2_exact(ts, pairs_dev, (const int32_t *)c->oti.p, first, n, *p, g, sc, (uint32_t *)c->crp.p,
+                                (float *)c->thr_q.p, (float *)c->thr_r.p, status, nullptr, st, &launches));
+        }
+        TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p,
+                           (const int32_t *)c->cols.p, n, g.max_cols, p->align, p->gamma_o, p->gamma_e,
+                           scores_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
+        if (dump && first == 0) {
+            // single-pair debug dump (K == 1)
+            const int q = 0;
+            (void)q;
+            if (dump->oti) CUDA_TRY(cudaMemcpyAsync(dump->oti, c->oti.p, 4, cudaMemcpyDeviceToHost, st));
+            int32_t rc[2];
+            CUDA_TRY(cudaMemcpyAsync(&rc[0], c->rows.p, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(&rc[1], c->cols.p, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const int wout = (rc[1] + 31) / 32;
+            if (dump->crp)
+                CUDA_TRY(cudaMemcpy2DAsync(dump->crp, (size_t)wout * 4, c->crp.p, (size_t)g.words * 4, (size_t)wout * 4,
+                                           rc[0], cudaMemcpyDeviceToHost, st));
+            if (dump->thr_q) CUDA_TRY(cudaMemcpyAsync(dump->thr_q, c->thr_q.p, (size_t)rc[0] * 4, cudaMemcpyDeviceToHost, st));
+            if (dump->thr_r) CUDA_TRY(cudaMemcpyAsync(dump->thr_r, c->thr_r.p, (size_t)rc[1] * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    // fold per-pair status into one word; read back at sync time
+    or_reduce_kernel<<<148, 256, 0, st>>>(status, K, (uint32_t *)c->misc.p);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+    CUDA_TRY(cudaMemcpyAsync(c->h_flag, c->misc.p, 4, cudaMemcpyDeviceToHost, st));
+    c->pending_status_check = 1;
+    c->pending_pairs = K;
+    c->stats[0] = K;
+    c->stats[2] = launches;
+    return ACOSS_OK;
+}
+
+int acoss_sync(acoss_ctx *c) {
+    if (!c) { acoss_set_error("NULL context"); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->pending_status_check) {
+        c->pending_status_check = 0;
+        if (c->h_flag[0] & PAIR_ST_NAN) {
+            acoss_set_error("a squared distance was negative -> NaN distance (essentia would raise: non-binary CRP, F7)");
+            return ACOSS_E_NAN;
+        }
+    }
+    return ACOSS_OK;
+}
+
+int acoss_score_pairs_device(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const acoss_params *p, float *scores_dev) {
+    if (!c || (K > 0 && (!pairs_dev || !scores_dev))) { acoss_set_error("score_pairs_device: NULL argument"); return ACOSS_E_INVALID; }
+    return run_pairs(c, pairs_dev, K, p, scores_dev, nullptr);
+}
+
+int acoss_score_pairs(acoss_ctx *c, const int32_t *pairs, int64_t K, const acoss_params *p, float *scores) {
+    if (!c || (K > 0 && (!pairs || !scores))) { acoss_set_error("score_pairs: NULL argument"); return ACOSS_E_INVALID; }
+    if (K <= 0) return check_params(c, p);
+    for (int64_t k = 0; k < 2 * K; ++k)
+        if (pairs[k] < 0 || pairs[k] >= c->n_tracks) { acoss_set_error("pair index %d out of range", pairs[k]); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(ensure(c->pairs, (size_t)K * 8));
+    TRY(ensure(c->scores, (size_t)K * 4));
+    CUDA_TRY(cudaMemcpyAsync(c->pairs.p, pairs, (size_t)K * 8, cudaMemcpyHostToDevice, c->stream));
+    TRY(run_pairs(c, (const int32_t *)c->pairs.p, K, p, (float *)c->scores.p, nullptr));
+    CUDA_TRY(cudaMemcpyAsync(scores, c->scores.p, (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
+    return acoss_sync(c);
+}
+
+int acoss_oti_pairs(acoss_ctx *c, const int32_t *pairs, int64_t K, int32_t noti, int32_t *oti) {
+    if (!c || !pairs || !oti || K < 0 || !c->d_frames) { acoss_set_error("oti_pairs: bad arguments"); return ACOSS_E_INVALID; }
+    if (K == 0) return ACOSS_OK;
+    for (int64_t k = 0; k < 2 * K; ++k)
+        if (pairs[k] < 0 || pairs[k] >= c->n_tracks) { acoss_set_error("pair index %d out of range", pairs[k]); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(ensure(c->pairs, (size_t)K * 8));
+    TRY(ensure(c->oti, (size_t)K * 4));
+    CUDA_TRY(cudaMemcpyAsync(c->pairs.p, pairs, (size_t)K * 8, cudaMemcpyHostToDevice, c->stream));
+    TRY(launch_oti(track_set(c), (const int32_t *)c->pairs.p, K, noti, 1, (int32_t *)c->oti.p, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(oti, c->oti.p, (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ACOSS_OK;
+}
+
+int acoss_dump_pair(acoss_ctx *c, int32_t q, int32_t r, const acoss_params *p, int32_t *oti, uint32_t *crp_bits,
+                    float *thr_q, float *thr_r, float *score) {
+    TRY(check_params(c, p));
+    if (q < 0 || r < 0 || q >= c->n_tracks || r >= c->n_tracks) { acoss_set_error("dump_pair: track index out of range"); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(ensure(c->pairs, 8));
+    TRY(ensure(c->scores, 4));
+    const int32_t pr[2] = {q, r};
+    CUDA_TRY(cudaMemcpyAsync(c->pairs.p, pr, 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    DumpOut d;
+    d.oti = oti; d.crp = crp_bits; d.thr_q = thr_q; d.thr_r = thr_r;
+    TRY(run_pairs(c, (const int32_t *)c->pairs.p, 1, p, (float *)c->scores.p, &d));
+    if (score) CUDA_TRY(cudaMemcpyAsync(score, c->scores.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    return acoss_sync(c);
+}
+
+int acoss_dp_bytes(acoss_ctx *c, const uint8_t *mats, const int64_t *offsets, const int32_t *shapes, int64_t n,
+                   int32_t mode, float gamma_o, float gamma_e, float *scores) {
+    if (!c || (n > 0 && (!mats || !offsets || !shapes || !scores))) { acoss_set_error("dp_bytes: NULL argument"); return ACOSS_E_INVALID; }
+    if (mode != ACOSS_ALIGN_QMAX && mode != ACOSS_ALIGN_SW) { acoss_set_error("dp_bytes: mode %d not implemented", mode); return ACOSS_E_INVALID; }
+    if (n == 0) return ACOSS_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int max_r = 1, max_c = 1;
+    int64_t total = 0;
+    for (int64_t k = 0; k < n; ++k) {
+        if (shapes[2 * k] < 0 || shapes[2 * k + 1] < 0 || shapes[2 * k] > (1 << 20) || shapes[2 * k + 1] > (1 << 20)) { acoss_set_error("dp_bytes: bad shape"); return ACOSS_E_INVALID; }
+        max_r = std::max(max_r, shapes[2 * k]);
+        max_c = std::max(max_c, shapes[2 * k + 1]);
+        total = std::max<int64_t>(total, offsets[k] + (int64_t)shapes[2 * k] * shapes[2 * k + 1]);
+    }
+    const int words = (max_c + 31) / 32 + 1;
+    const int64_t slot_words = (int64_t)max_r * words;
+    const size_t per_slot = (size_t)slot_words * 4 + (size_t)2 * max_r * 16 + 16;
+    int64_t slots = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n, 16384), c->ws_limit / (int64_t)per_slot));
+    Buf dm, doff, dsh;
+    int rc = ACOSS_OK;
+    auto cleanup = [&]() { free_buf(dm); free_buf(doff); free_buf(dsh); };
+#define TRYC(x) do { rc = (x); if (rc != ACOSS_OK) { cleanup(); return rc; } } while (0)
+#define CUDA_TRYC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { acoss_set_error("%s -> %s", #x, cudaGetErrorString(_e)); cleanup(); return ACOSS_E_CUDA; } } while (0)
+    TRYC(ensure(dm, (size_t)total + 16));
+    TRYC(ensure(doff, (size_t)n * 8));
+    TRYC(ensure(dsh, (size_t)n * 8));
+    TRYC(ensure(c->crp, (size_t)slots * slot_words * 4));
+    TRYC(ensure(c->rows, (size_t)slots * 4));
+    TRYC(ensure(c->cols, (size_t)slots * 4));
+    TRYC(ensure(c->halo, (size_t)slots * 2 * max_r * 16));
+    TRYC(ensure(c->scores, (size_t)n * 4));
+    TRYC(ensure(c->misc, 256));
+    CUDA_TRYC(cudaMemsetAsync(c->misc.p, 0, 256, st));
+    CUDA_TRYC(cudaMemcpyAsync(dm.p, mats, (size_t)total, cudaMemcpyHostToDevice, st));
+    CUDA_TRYC(cudaMemcpyAsync(doff.p, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRYC(cudaMemcpyAsync(dsh.p, shapes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    int64_t launches = 0;
+    for (int64_t first = 0; first < n; first += slots) {
+        const int nn = (int)std::min<int64_t>(slots, n - first);
+        TRYC(launch_pack_bytes((const uint8_t *)dm.p, (const int64_t *)doff.p + first, (const int32_t *)dsh.p + 2 * first, nn,
+                               mode, (uint32_t *)c->crp.p, slot_words, words, (int32_t *)c->rows.p, (int32_t *)c->cols.p,
+                               (uint32_t *)c->misc.p, st));
+        TRYC(launch_dp_bits((const uint32_t *)c->crp.p, slot_words, words, (const int32_t *)c->rows.p, (const int32_t *)c->cols.p,
+                            nn, max_c, mode, gamma_o, gamma_e, (float *)c->scores.p + first, (uint32_t *)c->halo.p, max_r, st,
+                            &launches));
+    }
+    CUDA_TRYC(cudaMemcpyAsync(scores, c->scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRYC(cudaMemcpyAsync(c->h_flag, c->misc.p, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRYC(cudaStreamSynchronize(st));
+    cleanup();
+#undef TRYC
+#undef CUDA_TRYC
+    if (c->h_flag[0]) { acoss_set_error("Non-binary elements found in input"); return ACOSS_E_NONBINARY; }
+    return ACOSS_OK;
+}
+
+int acoss_knn_sw(acoss_ctx *c, const double *csms, const int64_t *offsets, const int32_t *shapes, const int32_t *nn,
+                 int64_t n, float *scores, uint32_t *bits_out) {
+    if (!c || (n > 0 && (!csms || !offsets || !shapes || !nn || !scores))) { acoss_set_error("knn_sw: NULL argument"); return ACOSS_E_INVALID; }
+    if (n == 0) return ACOSS_OK;
+    if (n > 60000) { acoss_set_error("knn_sw: at most 60000 matrices per call"); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int max_r = 1, max_c = 1;
+    int64_t total = 0, out_total = 0;
+    std::vector<int64_t> out_off(n);
+    for (int64_t k = 0; k < n; ++k) {
+        const int M = shapes[2 * k], N = shapes[2 * k + 1];
+        if (M <= 0 || N <= 0 || M > 65535 || N > (1 << 20)) { acoss_set_error("knn_sw: bad shape"); return ACOSS_E_INVALID; }
+        if (nn[k] > N) { acoss_set_error("knn_sw: nn > columns (np.argpartition would raise)"); return ACOSS_E_INVALID; }
+        max_r = std::max(max_r, M); max_c = std::max(max_c, N);
+        total = std::max<int64_t>(total, offsets[k] + (int64_t)M * N);
+        out_off[k] = out_total;
+        out_total += (int64_t)M * ((N + 31) / 32);
+    }
+    const int words = (max_c + 31) / 32 + 1;
+    const int64_t slot_words = (int64_t)max_r * words;
+    Buf dcsm, doff, dsh, dnn, dout, dooff;
+    int rc = ACOSS_OK;
+    auto cleanup = [&]() { free_buf(dcsm); free_buf(doff); free_buf(dsh); free_buf(dnn); free_buf(dout); free_buf(dooff); };
+#define TRYC(x) do { rc = (x); if (rc != ACOSS_OK) { cleanup(); return rc; } } while (0)
+#define CUDA_TRYC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { acoss_set_error("%s -> %s", #x, cudaGetErrorString(_e)); cleanup(); return ACOSS_E_CUDA; } } while (0)
+    TRYC(ensure(dcsm, (size_t)total * 8));
+    TRYC(ensure(doff, (size_t)n * 8)); TRYC(ensure(dsh, (size_t)n * 8)); TRYC(ensure(dnn, (size_t)n * 4));
+    TRYC(ensure(dooff, (size_t)n * 8));
+    if (bits_out) TRYC(ensure(dout, (size_t)out_total * 4));
+    TRYC(ensure(c->crp, (size_t)n * slot_words * 4));
+    TRYC(ensure(c->rows, (size_t)n * 4)); TRYC(ensure(c->cols, (size_t)n * 4));
+    TRYC(ensure(c->halo, (size_t)n * 2 * max_r * 16));
+    TRYC(ensure(c->scores, (size_t)n * 4));
+    CUDA_TRYC(cudaMemcpyAsync(dcsm.p, csms, (size_t)total * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRYC(cudaMemcpyAsync(doff.p, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRYC(cudaMemcpyAsync(dsh.p, shapes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRYC(cudaMemcpyAsync(dnn.p, nn, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRYC(cudaMemcpyAsync(dooff.p, out_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRYC(cudaMemsetAsync(c->crp.p, 0, (size_t)n * slot_words * 4, st));
+    TRYC(launch_knn_rows((const double *)dcsm.p, (const int64_t *)doff.p, (const int32_t *)dsh.p, (const int32_t *)dnn.p, (int)n,
+                         max_r, max_c, (uint32_t *)c->crp.p, slot_words, words, bits_out ? (uint32_t *)dout.p : nullptr,
+                         (const int64_t *)dooff.p, (int32_t *)c->rows.p, (int32_t *)c->cols.p, st));
+    int64_t launches = 0;
+    TRYC(launch_dp_bits((const uint32_t *)c->crp.p, slot_words, words, (const int32_t *)c->rows.p, (const int32_t *)c->cols.p,
+                        (int)n, max_c, ACOSS_ALIGN_SW, 0.5f, 0.5f, (float *)c->scores.p, (uint32_t *)c->halo.p, max_r, st, &launches));
+    CUDA_TRYC(cudaMemcpyAsync(scores, c->scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (bits_out) CUDA_TRYC(cudaMemcpyAsync(bits_out, dout.p, (size_t)out_total * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRYC(cudaStreamSynchronize(st));
+    cleanup();
+#undef TRYC
+#undef CUDA_TRYC
+    return ACOSS_OK;
+}
+
+int acoss_last_stats(acoss_ctx *c, int64_t stats[8]) {
+    if (!c || !stats) { acoss_set_error("last_stats: NULL argument"); return ACOSS_E_INVALID; }
+    memcpy(stats, c->stats, sizeof(c->stats));
+    return ACOSS_OK;
+}
+
+}  // extern "C"

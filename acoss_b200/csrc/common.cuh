@@ -1,0 +1,97 @@
+// Shared declarations for the acoss_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/acoss_b200.h"
+
+#define NBINS ACOSS_NBINS
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (thread-local message, no exceptions across the ABI)
+// ---------------------------------------------------------------------------------------------
+void acoss_set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            acoss_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? ACOSS_E_NOMEM : ACOSS_E_CUDA;            \
+        }                                                                                       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Device-side description of the resident track set (HBM layout)
+// ---------------------------------------------------------------------------------------------
+struct TrackSet {
+    const float *frames;      // [total_frames][12] float32, 48 B per frame (16 B aligned)
+    const int64_t *offsets;   // [n_tracks + 1] first frame of each track
+    const float *gchroma;     // [n_tracks][12] global chroma: sequential f32 frame sum / max (App. A1)
+    int32_t n_tracks;
+    int32_t max_frames;
+};
+
+// Per-pair status bits written by the kernels
+#define PAIR_ST_NAN 1u        // a NaN distance was produced (F7)
+#define PAIR_ST_FALLBACK 2u   // the fast CRP path failed a consistency check; exact path re-ran it
+
+// One work slot of the pair pipeline (fixed pitch so no device-side scan is needed)
+struct SlotGeom {
+    int32_t max_rows;     // max M' over the call
+    int32_t max_cols;     // max N' over the call
+    int32_t words;        // CRP row pitch in 32-bit words (ceil(max_cols/32) + 1 pad word)
+    int64_t crp_words;    // words per slot = max_rows * words
+};
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rot_src(int b, int s) {   // rotR(x, s)[b] = x[(b - s) mod 12]
+    int k = b - s;
+    return k < 0 ? k + NBINS : k;
+}
+
+// essentia dotProduct arithmetic (App. A3, F3): float32 product (one rounding), sequential
+// float64 accumulate.  __fmul_rn / __dadd_rn block FMA contraction.
+__device__ __forceinline__ double acc_f32prod(double acc, float a, float b) {
+    return __dadd_rn(acc, (double)__fmul_rn(a, b));
+}
+
+// host launchers (one per translation unit) -----------------------------------------------------
+struct Params;   // fwd
+
+int launch_global_chroma(const float *frames, const int64_t *offsets, int n_tracks, float *gchroma,
+                         cudaStream_t st);
+int launch_oti(const TrackSet &ts, const int32_t *pairs, int64_t n_pairs, int noti, int apply,
+               int32_t *oti_out, cudaStream_t st);
+
+// K2 exact path: CRP bits + thresholds for `n` pairs (pairs[first..first+n)) into slots 0..n-1
+struct ExactScratch {
+    float *rrot;     // [slots][max_frames][12] rotated reference frames
+    float *aa;       // [slots][max_rows]
+    float *bb;       // [slots][max_cols]
+    float *D;        // [slots][max_rows][ldd] float32 distances
+    int64_t ldd;
+    int32_t slots;
+};
+int launch_k2_exact(const TrackSet &ts, const int32_t *pairs, const int32_t *oti, int64_t first, int n,
+                    const acoss_params &p, const SlotGeom &g, const ExactScratch &sc,
+                    uint32_t *crp, float *thr_q, float *thr_r, uint32_t *status,
+                    const int32_t *slot_pair_map, cudaStream_t st, int64_t *launches);
+
+// K3: alignment DP over bit-packed matrices.  rows[k], cols[k] give the DP matrix of slot k.
+int launch_dp_bits(const uint32_t *bits, int64_t slot_words, int words_per_row, const int32_t *rows,
+                   const int32_t *cols, int n, int max_cols, int mode, float gamma_o, float gamma_e,
+                   float *scores, uint32_t *halo_scratch, int64_t halo_pitch, cudaStream_t st,
+                   int64_t *launches);
+// pair geometry (rows = n_q - m*tau, cols = n_r - m*tau) for pairs[first..first+n)
+int launch_pair_geometry(const TrackSet &ts, const int32_t *pairs, int64_t first, int n, int incr,
+                         int32_t *rows, int32_t *cols, cudaStream_t st);
+int launch_pack_bytes(const uint8_t *mats, const int64_t *offsets, const int32_t *shapes, int n,
+                      int mode, uint32_t *bits, int64_t slot_words, int words_per_row,
+                      int32_t *rows, int32_t *cols, uint32_t *nonbinary_flag, cudaStream_t st);
+int launch_knn_rows(const double *csms, const int64_t *offsets, const int32_t *shapes, const int32_t *nn, int n,
+                    int max_rows, int max_cols, uint32_t *bits_dp, int64_t slot_words, int wpr, uint32_t *bits_out,
+                    const int64_t *out_offsets, int32_t *rows, int32_t *cols, cudaStream_t st);

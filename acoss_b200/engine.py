@@ -1,0 +1,162 @@
+"""Thin host wrapper over the C ABI: one Engine = one acoss_ctx on one CUDA device.
+
+PyTorch appears only as an optional way to hand over device memory (``data_ptr()``); all
+arithmetic runs in the CUDA kernels of libacoss_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ALIGN_QMAX, ALIGN_SW, AcossError, Params, check, default_params  # noqa: F401
+
+__all__ = ["Engine", "AcossError", "default_params", "pack_tracks"]
+
+
+def pack_tracks(tracks):
+    """list of (n_i, 12) arrays -> (frames float32 [sum n_i, 12] C-contiguous, offsets int64)."""
+    lens = [int(t.shape[0]) for t in tracks]
+    for t in tracks:
+        if t.ndim != 2 or t.shape[1] != 12:
+            raise ValueError("every track must be (n_frames, 12); got %r" % (t.shape,))
+    offsets = np.zeros(len(tracks) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    frames = np.empty((int(offsets[-1]), 12), dtype=np.float32)
+    for t, o in zip(tracks, offsets[:-1]):
+        frames[o:o + t.shape[0]] = t            # handles the reference's transposed views
+    return frames, offsets
+
+
+class Engine:
+    def __init__(self, device: int = 0, workspace_bytes: int | None = None):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        check(self._lib.acoss_create(C.byref(self._ctx), int(device)))
+        self.device = int(device)
+        self.n_tracks = 0
+        self.offsets = None
+        self._keepalive = None
+        if workspace_bytes is not None:
+            check(self._lib.acoss_set_workspace_limit(self._ctx, int(workspace_bytes)))
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.acoss_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- tracks ---------------------------------------------------------------------------------
+    def set_tracks(self, frames, offsets):
+        """frames: float32 (total, 12) numpy array (host) or CUDA torch tensor (adopted, not copied)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        if hasattr(frames, "data_ptr"):                       # torch tensor hand-off
+            if not frames.is_cuda or frames.dtype.__str__() != "torch.float32" or not frames.is_contiguous():
+                raise ValueError("device frames must be a contiguous float32 CUDA tensor")
+            if frames.numel() != int(offsets[-1]) * 12:
+                raise ValueError("frames size does not match offsets")
+            self._keepalive = frames
+            check(self._lib.acoss_set_tracks(self._ctx, frames.data_ptr(), offsets.ctypes.data, n, 1))
+        else:
+            frames = np.ascontiguousarray(frames, dtype=np.float32)
+            if frames.size != int(offsets[-1]) * 12:
+                raise ValueError("frames size does not match offsets")
+            self._keepalive = None
+            check(self._lib.acoss_set_tracks(self._ctx, frames.ctypes.data, offsets.ctypes.data, n, 0))
+        self.n_tracks = n
+        self.offsets = offsets
+
+    # -- scoring --------------------------------------------------------------------------------
+    def score_pairs(self, pairs, params: Params | None = None) -> np.ndarray:
+        """Host in / host out (the end-to-end path): pairs (K, 2) int -> scores float32 (K,)."""
+        params = params or default_params()
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.empty(len(pairs), dtype=np.float32)
+        check(self._lib.acoss_score_pairs(self._ctx, pairs.ctypes.data, len(pairs), C.byref(params),
+                                          out.ctypes.data))
+        return out
+
+    def score_pairs_device(self, pairs_ptr: int, n_pairs: int, scores_ptr: int, params: Params | None = None):
+        """Device in / device out, asynchronous on the engine stream; call sync()."""
+        params = params or default_params()
+        check(self._lib.acoss_score_pairs_device(self._ctx, pairs_ptr, int(n_pairs), C.byref(params), scores_ptr))
+
+    def sync(self):
+        check(self._lib.acoss_sync(self._ctx))
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._lib.acoss_stream(self._ctx) or 0)
+
+    def oti_pairs(self, pairs, noti: int = 12) -> np.ndarray:
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.empty(len(pairs), dtype=np.int32)
+        check(self._lib.acoss_oti_pairs(self._ctx, pairs.ctypes.data, len(pairs), int(noti), out.ctypes.data))
+        return out
+
+    def dump_pair(self, q: int, r: int, params: Params | None = None):
+        """-> dict(oti, crp uint8 (M', N'), thr_q, thr_r, score) for one pair (debug API)."""
+        params = params or default_params()
+        incr = params.m * params.tau
+        M = int(self.offsets[q + 1] - self.offsets[q]) - incr
+        N = int(self.offsets[r + 1] - self.offsets[r]) - incr
+        if M < 2 or N < 2:
+            # let the library produce the reference-shaped error
+            check(self._lib.acoss_dump_pair(self._ctx, q, r, C.byref(params), None, None, None, None, None))
+        W = (N + 31) // 32
+        oti = C.c_int32(0)
+        score = C.c_float(0)
+        bits = np.zeros((M, W), dtype=np.uint32)
+        tq = np.zeros(M, dtype=np.float32)
+        tr = np.zeros(N, dtype=np.float32)
+        check(self._lib.acoss_dump_pair(self._ctx, q, r, C.byref(params), C.addressof(oti), bits.ctypes.data,
+                                        tq.ctypes.data, tr.ctypes.data, C.addressof(score)))
+        crp = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :N]
+        return dict(oti=int(oti.value), crp=crp, bits=bits, thr_q=tq, thr_r=tr, score=float(score.value))
+
+    def dp_bytes(self, mats, mode: int = ALIGN_SW, gamma_o: float = 0.5, gamma_e: float = 0.5) -> np.ndarray:
+        """Batched alignment DP over binary uint8 matrices (K3 only)."""
+        mats = [np.ascontiguousarray(m) for m in mats]
+        for m in mats:
+            if m.ndim != 2:
+                raise ValueError("matrices must be 2-D")
+        # values other than 0/1 must reach the kernel's validation: clip into uint8 keeping >1 as 2
+        conv = []
+        for m in mats:
+            if m.dtype != np.uint8:
+                mm = np.where(m == 0, 0, np.where(m == 1, 1, 2)).astype(np.uint8)
+            else:
+                mm = m
+            conv.append(mm)
+        shapes = np.array([m.shape for m in conv], dtype=np.int32).reshape(-1, 2)
+        sizes = np.array([m.size for m in conv], dtype=np.int64)
+        offs = np.zeros(len(conv), dtype=np.int64)
+        if len(conv) > 1:
+            offs[1:] = np.cumsum(sizes)[:-1]
+        buf = np.concatenate([m.ravel() for m in conv]) if conv else np.zeros(0, np.uint8)
+        if buf.size == 0:
+            buf = np.zeros(1, np.uint8)
+        out = np.zeros(len(conv), dtype=np.float32)
+        check(self._lib.acoss_dp_bytes(self._ctx, buf.ctypes.data, offs.ctypes.data, shapes.ctypes.data,
+                                       len(conv), int(mode), float(gamma_o), float(gamma_e), out.ctypes.data))
+        return out
+
+    def last_stats(self) -> dict:
+        st = np.zeros(8, dtype=np.int64)
+        check(self._lib.acoss_last_stats(self._ctx, st.ctypes.data))
+        return dict(pairs=int(st[0]), fallback_pairs=int(st[1]), launches=int(st[2]), cells=int(st[3]),
+                    exact_cells=int(st[4]))

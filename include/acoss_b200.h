@@ -1,0 +1,133 @@
+/* acoss_b200 — C ABI of the B200-native all-pairs cover-song scoring hot path.
+ *
+ * Drop-in boundary.  The reference (furkanyesiler/acoss) has no FFI of its own: its hot path is
+ * the body of a Python plugin method that calls two essentia C++ algorithms per pair,
+ *     acoss/algorithms/rqa_serra09.py:55-69        Serra09.similarity(idxs)
+ *     acoss/algorithms/rqa_serra09.py:60-67        ChromaCrossSimilarity(...)(query, reference)
+ *                                                  CoverSongSimilarity('serra09','symmetric')(csm)
+ * and, for the EarlyFusion flavour, the in-tree numba kernels
+ *     acoss/algorithms/utils/alignment_tools.py:26-46     smith_waterman_constrained(B)
+ *     acoss/algorithms/utils/cross_recurrence.py:76-103   get_oti(C1, C2)
+ *     acoss/algorithms/utils/cross_recurrence.py:137-161  csm_to_binary(D, kappa)
+ * Each entry point below names the reference interface it replaces.  A maintainer binds them
+ * with ctypes; acoss_b200/_lib.py is that binding.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every function returns 0 on success or a
+ * negative ACOSS_E_* code, with a human-readable message available from acoss_last_error()
+ * (thread-local).  No exceptions cross the ABI.  One context per device; a context is not
+ * thread-safe.  There is NO CPU fallback: every entry point fails with ACOSS_E_CUDA when no
+ * sm_100-class device is usable.
+ */
+#ifndef ACOSS_B200_H
+#define ACOSS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACOSS_OK 0
+#define ACOSS_E_INVALID (-1)    /* bad argument                                                    */
+#define ACOSS_E_CUDA (-2)       /* CUDA runtime error / no device                                  */
+#define ACOSS_E_TOO_SHORT (-3)  /* a track has fewer than m*tau+2 frames (essentia throws; F9)     */
+#define ACOSS_E_NAN (-4)        /* a squared distance was negative -> NaN (essentia: non-binary)   */
+#define ACOSS_E_NONBINARY (-5)  /* DP input holds values other than 0/1 (reference: IOError)       */
+#define ACOSS_E_NOMEM (-6)      /* device memory exhausted                                         */
+
+#define ACOSS_NBINS 12          /* chroma bins per HPCP frame (rqa_serra09.py: 12-bin HPCP)        */
+
+/* alignment recurrences (acoss_params.align / acoss_dp_* mode) */
+#define ACOSS_ALIGN_QMAX 0      /* essentia CoverSongSimilarity alignmentType='serra09'            */
+#define ACOSS_ALIGN_SW 1        /* alignment_tools.py:26-46 smith_waterman_constrained             */
+#define ACOSS_ALIGN_DMAX 2      /* essentia alignmentType='chen17' (latefusion_chen.py:69-71)      */
+
+/* CRP construction path (acoss_params.crp_path) */
+#define ACOSS_CRP_AUTO 0        /* fast sweep kernels, exact per-pair fallback when a check fails  */
+#define ACOSS_CRP_EXACT 1       /* exact reference-order kernels only (slow; debugging / fallback) */
+
+typedef struct acoss_ctx acoss_ctx;
+
+/* Parameters of Serra09.__init__ (rqa_serra09.py:31-32) + essentia defaults. */
+typedef struct acoss_params {
+    int32_t m;              /* frameStackSize, 9                                                   */
+    int32_t tau;            /* frameStackStride, 1                                                 */
+    float kappa;            /* binarizePercentile, 0.095                                           */
+    int32_t oti;            /* 1: transpose the reference by the optimal transposition index       */
+    int32_t noti;           /* 12                                                                  */
+    float gamma_o;          /* disOnset, 0.5                                                       */
+    float gamma_e;          /* disExtension, 0.5                                                   */
+    int32_t align;          /* ACOSS_ALIGN_QMAX (Serra09) or ACOSS_ALIGN_DMAX (ChenFusion)         */
+    int32_t integer_guard;  /* F1 switch: 0 = essentia behaviour (integer rank -> threshold 0)     */
+    int32_t crp_path;       /* ACOSS_CRP_AUTO / ACOSS_CRP_EXACT                                    */
+} acoss_params;
+
+/* Fills *p with the reference defaults (m=9, tau=1, kappa=0.095, oti=1, noti=12, 0.5, 0.5, Qmax). */
+void acoss_default_params(acoss_params *p);
+
+const char *acoss_last_error(void);
+/* Library version string, and the sm target the kernels were compiled for (100). */
+const char *acoss_version(void);
+int acoss_compiled_sm(void);
+
+/* Context on CUDA device `device` (its primary context; torch tensors of the same device can be
+ * passed as raw pointers). */
+int acoss_create(acoss_ctx **ctx, int device);
+int acoss_destroy(acoss_ctx *ctx);
+/* Upper bound, in bytes, of per-call scratch the context may allocate (default 24 GiB). */
+int acoss_set_workspace_limit(acoss_ctx *ctx, int64_t bytes);
+
+/* Replaces the per-process feature cache Serra09.all_feats / load_features (rqa_serra09.py:44-53):
+ * uploads (or adopts, when frames_on_device != 0 — the pointer must stay valid) all tracks'
+ * post-downsampling HPCP frames, concatenated: frames[(offsets[t] + f) * 12 + bin], float32;
+ * offsets has n_tracks + 1 entries (host memory).  Precomputes the per-track global chroma. */
+int acoss_set_tracks(acoss_ctx *ctx, const float *frames, const int64_t *offsets, int32_t n_tracks,
+                     int frames_on_device);
+
+/* Replaces Serra09.similarity(idxs) (rqa_serra09.py:55-69) for a whole batch: pairs[2k] = query
+ * track, pairs[2k+1] = reference track; scores[k] = the float the reference stores in
+ * Ds[key][i][j].  Host buffers; H2D of the pair list and D2H of the scores happen inside. */
+int acoss_score_pairs(acoss_ctx *ctx, const int32_t *pairs, int64_t n_pairs, const acoss_params *p,
+                      float *scores);
+/* Same with DEVICE buffers (pairs and scores in HBM), asynchronous on the context's stream;
+ * acoss_sync() waits for it.  Used for device-resident timing and for NCCL hand-off. */
+int acoss_score_pairs_device(acoss_ctx *ctx, const int32_t *pairs_dev, int64_t n_pairs,
+                             const acoss_params *p, float *scores_dev);
+int acoss_sync(acoss_ctx *ctx);
+/* Returns the context's CUDA stream (a cudaStream_t) so callers can record events on it. */
+void *acoss_stream(acoss_ctx *ctx);
+
+/* K1 only — essentia optimalTranspositionIndex (inside ChromaCrossSimilarity, App. A1). */
+int acoss_oti_pairs(acoss_ctx *ctx, const int32_t *pairs, int64_t n_pairs, int32_t noti, int32_t *oti);
+
+/* Debug dump of one pair (query track q, reference track r): OTI, bit-packed CRP
+ * (rows = n_q - m*tau, words_per_row = ceil((n_r - m*tau)/32), bit b of word w = column 32w+b),
+ * thresholds and the alignment score.  Any output pointer may be NULL.  Host buffers. */
+int acoss_dump_pair(acoss_ctx *ctx, int32_t q, int32_t r, const acoss_params *p, int32_t *oti,
+                    uint32_t *crp_bits, float *thr_q, float *thr_r, float *score);
+
+/* K3 only — batched alignment DP over caller-supplied binary matrices (uint8, row-major, back to
+ * back: matrix k starts at mats[offsets[k]], shape (shapes[2k], shapes[2k+1])).  Host buffers.
+ *   ACOSS_ALIGN_SW   replaces smith_waterman_constrained(B) (alignment_tools.py:26-46)
+ *   ACOSS_ALIGN_QMAX replaces CoverSongSimilarity('serra09','symmetric')(csm)[1]
+ *   ACOSS_ALIGN_DMAX replaces CoverSongSimilarity('chen17','symmetric')(csm)[1]
+ * Non-binary input -> ACOSS_E_NONBINARY (reference raises IOError / EssentiaException). */
+int acoss_dp_bytes(acoss_ctx *ctx, const uint8_t *mats, const int64_t *offsets, const int32_t *shapes,
+                   int64_t n_mats, int32_t mode, float gamma_o, float gamma_e, float *scores);
+
+/* Row-only k-NN binarisation + SW of caller-supplied float64 CSMs — replaces
+ * smith_waterman_constrained(csm_to_binary(D, kappa)) (earlyfusion_traile.py:168,171,175,183).
+ * nn[k] = neighbours per row for matrix k (cross_recurrence.py:151-155 rule, computed by the
+ * host).  bits_out (may be NULL) receives the bit-packed binary matrices back to back
+ * (rows * ceil(cols/32) words each).  Ties at the nn-th value: lowest column index first. */
+int acoss_knn_sw(acoss_ctx *ctx, const double *csms, const int64_t *offsets, const int32_t *shapes,
+                 const int32_t *nn, int64_t n_mats, float *scores, uint32_t *bits_out);
+
+/* Counters of the last acoss_score_pairs* call: [0] pairs, [1] pairs that took the exact
+ * fallback, [2] kernel launches, [3] cells (sum of M'*N'), [4] exact re-evaluated candidate cells. */
+int acoss_last_stats(acoss_ctx *ctx, int64_t stats[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACOSS_B200_H */

@@ -1,0 +1,58 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol the header
+declares, and fails loudly (no CPU fallback) when no device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from acoss_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "acoss_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(acoss_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libacoss_b200.so does not export %s" % n
+    assert sorted(_lib.SIGNATURES) == names, "python binding and header disagree"
+
+
+def test_params_struct_matches_defaults():
+    p = _lib.default_params()
+    assert (p.m, p.tau, p.oti, p.noti, p.align, p.integer_guard, p.crp_path) == (9, 1, 1, 12, 0, 0, 0)
+    assert abs(p.kappa - 0.095) < 1e-7 and p.gamma_o == 0.5 and p.gamma_e == 0.5
+    assert C.sizeof(_lib.Params) == 40
+    assert _lib.load().acoss_compiled_sm() == 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from acoss_b200 import AcossError, Engine
+    with pytest.raises(AcossError) as ei:
+        Engine(0)
+    assert ei.value.code == _lib.E_CUDA and "no CPU fallback" in str(ei.value)
+
+
+def test_sass_is_sm100_with_dpx():
+    """The shipped cubin targets sm_100a and the DP kernel uses the packed DPX instructions."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", "dp_packed_kernel", _lib.LIB_PATH],
+                         capture_output=True, text=True).stdout
+    if "dp_packed_kernel" not in out:        # older cuobjdump: filter by hand
+        out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100" in out
+    assert "VIMNMX3.S16x2" in out and "VIADDMNMX.S16x2.RELU" in out
