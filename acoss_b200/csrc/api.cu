@@ -45,7 +45,40 @@ struct acoss_ctx {
     int64_t stats[8] = {0};
     int pending_status_check = 0;
     int64_t pending_pairs = 0;
+    // optional per-stage timing (CUDA events on the context stream)
+    int profiling = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double stage_ms[4] = {0, 0, 0, 0};
 };
+
+static cudaEvent_t get_event(acoss_ctx *c) {
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[c->ev_used++];
+}
+struct StageTimer {     // records [a, b] around a pipeline stage when profiling is on
+    acoss_ctx *c; int stage; cudaEvent_t a = nullptr;
+    StageTimer(acoss_ctx *c_, int s) : c(c_), stage(s) {
+        if (c->profiling) { a = get_event(c); cudaEventRecord(a, c->stream); }
+    }
+    void stop() {
+        if (c->profiling && a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({stage, a, b}); a = nullptr; }
+    }
+};
+static void fold_spans(acoss_ctx *c) {
+    for (auto &s : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) c->stage_ms[s.stage] += ms;
+    }
+    c->spans.clear();
+    c->ev_used = 0;
+}
 
 static int ensure(Buf &b, size_t bytes) {
     if (bytes <= b.cap) return ACOSS_OK;
@@ -121,6 +154,7 @@ int acoss_destroy(acoss_ctx *c) {
     if (c->d_offsets) cudaFree(c->d_offsets);
     if (c->d_gchroma) cudaFree(c->d_gchroma);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
     return ACOSS_OK;
@@ -239,7 +273,11 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     TRY(ensure(c->misc, 256));
     CUDA_TRY(cudaMemsetAsync(c->status.p, 0, (size_t)K * 4 + 64, st));
     CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 256, st));
-    TRY(launch_oti(ts, pairs_dev, K, p->noti, p->oti, (int32_t *)c->oti.p, st));
+    {
+        StageTimer t1(c, 0);
+        TRY(launch_oti(ts, pairs_dev, K, p->noti, p->oti, (int32_t *)c->oti.p, st));
+        t1.stop();
+    }
     ++launches;
 
     const bool fast = (p->crp_path == ACOSS_CRP_AUTO) && k2_fast_supported(*p, g);
@@ -274,6 +312,7 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
         const int n = (int)std::min<int64_t>(slots, K - first);
         TRY(launch_pair_geometry(ts, pairs_dev, first, n, incr, (int32_t *)c->rows.p, (int32_t *)c->cols.p, st));
         ++launches;
+        StageTimer t2(c, 1);
         if (fast) {
             TRY(launch_k2_fast(ts, pairs_dev, (const int32_t *)c->oti.p, first, n, *p, g, c->fast.p, fast_slot,
                                (uint32_t *)c->crp.p, (float *)c->thr_q.p, (float *)c->thr_r.p, status, st, &launches));
@@ -294,9 +333,12 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
             TRY(launch_k2_exact(ts, pairs_dev, (const int32_t *)c->oti.p, first, n, *p, g, sc, (uint32_t *)c->crp.p,
                                 (float *)c->thr_q.p, (float *)c->thr_r.p, status, nullptr, st, &launches));
         }
+        t2.stop();
+        StageTimer t3(c, 2);
         TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p,
                            (const int32_t *)c->cols.p, n, g.max_cols, p->align, p->gamma_o, p->gamma_e,
                            scores_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
+        t3.stop();
         if (dump && first == 0) {
             // single-pair debug dump (K == 1)
             const int q = 0;
@@ -331,6 +373,7 @@ int acoss_sync(acoss_ctx *c) {
     if (!c) { acoss_set_error("NULL context"); return ACOSS_E_INVALID; }
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fold_spans(c);
     if (c->pending_status_check) {
         c->pending_status_check = 0;
         if (c->h_flag[0] & PAIR_ST_NAN) {
@@ -501,6 +544,25 @@ int acoss_knn_sw(acoss_ctx *c, const double *csms, const int64_t *offsets, const
     cleanup();
 #undef TRYC
 #undef CUDA_TRYC
+    return ACOSS_OK;
+}
+
+int acoss_set_profiling(acoss_ctx *c, int on) {
+    if (!c) { acoss_set_error("NULL context"); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fold_spans(c);
+    c->profiling = on ? 1 : 0;
+    for (double &m : c->stage_ms) m = 0.0;
+    return ACOSS_OK;
+}
+
+int acoss_stage_ms(acoss_ctx *c, double ms[4]) {
+    if (!c || !ms) { acoss_set_error("stage_ms: NULL argument"); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fold_spans(c);
+    for (int i = 0; i < 4; ++i) ms[i] = c->stage_ms[i];
     return ACOSS_OK;
 }
 

@@ -155,6 +155,15 @@ class Engine:
                                        len(conv), int(mode), float(gamma_o), float(gamma_e), out.ctypes.data))
         return out
 
+    def set_profiling(self, on: bool = True):
+        check(self._lib.acoss_set_profiling(self._ctx, int(bool(on))))
+
+    def stage_ms(self) -> dict:
+        """Accumulated CUDA-event milliseconds per pipeline stage since set_profiling(True)."""
+        ms = np.zeros(4, dtype=np.float64)
+        check(self._lib.acoss_stage_ms(self._ctx, ms.ctypes.data))
+        return dict(k1_oti=float(ms[0]), k2_crp=float(ms[1]), k3_dp=float(ms[2]))
+
     def last_stats(self) -> dict:
         st = np.zeros(8, dtype=np.int64)
         check(self._lib.acoss_last_stats(self._ctx, st.ctypes.data))

@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — all-pairs Serra09 scoring throughput (alignments/s, GCUPS) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch P] [--impl reference]
+
+Workload (BASELINE.json configs[2], "C3"): synthetic 1 000-track Da-TACOS-shaped slice, 12-bin
+HPCP, ~2k frames/track, 499 500 unique (i<j) pairs.  A *step* is one pass of the hot path
+(K1 OTI -> K2 CRP -> K3 Qmax) over one batch of P consecutive pairs of that pair list; at N>1 the
+pair list is sharded across ranks (weak scaling: every rank does K steps of P pairs of its own
+shard, no data-path collective) and the per-rank score tiles are gathered with one NCCL
+all_gather at the end of the timed region.
+
+Output: ONE JSON line on rank 0 (contract in the task statement), with
+  value        device-resident throughput (pairs and scores in HBM, CUDA events, max over ranks)
+  e2e          the same metric through the plugin API Serra09.similarity(idxs): host pair list in,
+               scores read back into the host score matrix, every step
+  roofline     dominant kernel stage (K2, CRP construction) against measured HBM bandwidth; the
+               stage is ALU-issue bound by design, so `roofline_alu` reports cell updates against
+               the lane-instruction issue peak as well
+  cpu_baseline the oracle's plain-C port of the reference CPU path (oracle/serra09_c.c), all host
+               threads, on a bounded sample of the same pairs
+`--impl reference` times that CPU port alone (the reference's essentia path cannot be installed:
+DESIGN.md §5) on the same config/metric/unit.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "all-pairs alignments/sec"
+UNIT = "pairs/s"
+WORKLOAD = "C3: Serra09 all-pairs, 1000 synthetic tracks x ~2k HPCP frames (499500 unique pairs)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback", 1965.0
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_dataset():
+    from acoss_b200 import pack_tracks, synthetic
+    tracks, labels = synthetic.config_dataset("C3")
+    frames, offs = pack_tracks(tracks)
+    pairs = synthetic.all_pairs_upper(len(tracks))
+    lens = np.diff(offs)
+    return tracks, labels, frames, offs, pairs, lens
+
+
+def algorithmic_bytes(lens, pairs, incr=9):
+    """48(n_q+n_r) frames in + M'N'/8 CRP out (K2) + M'N'/8 CRP in (K3) + 4 score."""
+    nq = lens[pairs[:, 0]].astype(np.int64); nr = lens[pairs[:, 1]].astype(np.int64)
+    cells = (nq - incr) * (nr - incr)
+    k2 = 48 * (nq + nr) + cells // 8
+    k3 = cells // 8 + 4
+    return int(cells.sum()), int(k2.sum()), int(k3.sum())
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU port of the reference path, all host threads, bounded steps."""
+    if rank != 0:
+        return
+    from oracle import serra09_c as oc
+    tracks, labels, frames, offs, pairs, lens = build_dataset()
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 8)
+    rng = np.random.default_rng(1234)
+    sel = rng.permutation(len(pairs))
+    p = oc.params()
+    k0 = 0
+    for _ in range(max(1, min(args.warmup, 1))):
+        oc.pairs(frames, offs, pairs[sel[k0:k0 + per_step]], p, nthreads=cores); k0 += per_step
+    t0 = time.perf_counter()
+    ncell = 0
+    for _ in range(args.steps):
+        idx = pairs[sel[k0:k0 + per_step]]; k0 += per_step
+        oc.pairs(frames, offs, idx, p, nthreads=cores)
+        ncell += algorithmic_bytes(lens, idx)[0]
+    dt = time.perf_counter() - t0
+    val = args.steps * per_step / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gcups": ncell / dt / 1e9,
+            "config": {"workload": WORKLOAD, "pairs_per_step": per_step,
+                       "note": "plain-C port of the reference CPU path (essentia ChromaCrossSimilarity + "
+                               "CoverSongSimilarity restated; essentia itself is not installable), pthreads over pairs"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d random C3 pairs per step, %d steps" % (per_step, args.steps)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=0, help="pairs per step (0 = auto)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--crp-path", default="auto", choices=["auto", "exact"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from acoss_b200 import Engine, default_params
+    from acoss_b200._lib import CRP_AUTO, CRP_EXACT
+    from acoss_b200.serra09 import Serra09
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_kind, sm_max = load_peaks()
+
+    tracks, labels, frames, offs, pairs, lens = build_dataset()
+    P = args.batch or (8192 if args.crp_path == "exact" else 32768)
+    total_steps = args.warmup + args.steps
+    # shard: rank r owns a contiguous region of a fixed random permutation of the pair list
+    perm = np.random.default_rng(99).permutation(len(pairs))
+    need = total_steps * P
+    if need * world > len(perm):
+        perm = np.concatenate([perm] * (need * world // len(perm) + 1))
+    mine = pairs[perm[rank * need:(rank + 1) * need]]
+    params = default_params(crp_path=CRP_EXACT if args.crp_path == "exact" else CRP_AUTO)
+
+    eng = Engine(local)
+    t0 = time.perf_counter()
+    eng.set_tracks(frames, offs)
+    setup_s = time.perf_counter() - t0
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=torch.device("cuda", local))
+    d_pairs = torch.from_numpy(mine.astype(np.int32)).cuda(local)
+    d_scores = torch.zeros(need, dtype=torch.float32, device="cuda:%d" % local)
+    gathered = torch.zeros(world * need, dtype=torch.float32, device="cuda:%d" % local) if world > 1 else None
+
+    def step(k):
+        eng.score_pairs_device(d_pairs[k * P:(k + 1) * P].data_ptr(), P, d_scores[k * P:(k + 1) * P].data_ptr(), params)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------------
+    for k in range(args.warmup):
+        step(k)
+    eng.sync()
+    eng.set_profiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for k in range(args.warmup, total_steps):
+            step(k)
+            launches += eng.last_stats()["launches"]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_scores)      # NCCL gather of the per-rank score tiles
+        ev1.record(stream)
+    eng.sync()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    stage = eng.stage_ms()
+    eng.set_profiling(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    timed = mine[args.warmup * P: total_steps * P]
+    cells, bytes_k2, bytes_k3 = algorithmic_bytes(lens, timed)
+    value = world * args.steps * P / (ms_max / 1e3)
+    gcups = world * cells / (ms_max / 1e3) / 1e9
+
+    # ---- end to end through the plugin API (host buffers in, host score matrix out) -----------
+    feats = [dict(hpcp=t_, label=str(l)) for t_, l in zip(tracks, labels)]
+    cache = os.path.join("/tmp", "acoss_bench_cache_%d" % rank)
+    alg = Serra09(None, None, features=feats, downsample_fac=1, shortname="bench%d" % rank, device=local,
+                  cachedir=cache, engine=eng)
+    alg._resident = True                                       # tracks already resident in this engine
+    alg.crp_path = params.crp_path
+    host_pairs = [mine[k * P:(k + 1) * P].astype(np.int64) for k in range(total_steps)]
+    for k in range(min(args.warmup, 2)):
+        alg.similarity(host_pairs[k])
+    barrier()
+    te0 = time.perf_counter()
+    for k in range(args.warmup, total_steps):
+        alg.similarity(host_pairs[k])
+    torch.cuda.synchronize()
+    te = time.perf_counter() - te0
+    t = torch.tensor([te], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * args.steps * P / float(t.item())
+    alg.cleanup_memmap()
+
+    # ---- roofline of the dominant stage (K2 = CRP construction) -------------------------------
+    k2_ms = stage["k2_crp"]
+    k3_ms = stage["k3_dp"]
+    n_k2_launch_groups = args.steps
+    ach_gbs = bytes_k2 / (k2_ms / 1e3) / 1e9 if k2_ms > 0 else None
+    sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+    issue_peak = 148 * 128 * sm_mhz * 1e6                      # lane-instructions / s at the measured clock
+    roofline = {"bound": "hbm", "kernel": "K2 CRP construction stage (k2_*)", "achieved": ach_gbs, "peak": hbm_peak,
+                "unit": "GB/s", "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "traffic": None,
+                "peak_kind": peak_kind, "algorithmic_bytes_per_step": bytes_k2 // args.steps,
+                "stage_ms_per_step": k2_ms / args.steps,
+                "note": "stage is ALU-issue bound by design (no float CSM in HBM); see roofline_alu"}
+    roofline_alu = {"k2_cells_per_s": cells / (k2_ms / 1e3) if k2_ms > 0 else None,
+                    "k3_cells_per_s": cells / (k3_ms / 1e3) if k3_ms > 0 else None,
+                    "issue_peak_lane_ops_per_s": issue_peak,
+                    "k2_lane_ops_per_cell_at_peak": issue_peak / (cells / (k2_ms / 1e3)) if k2_ms > 0 else None,
+                    "k3_frac_of_5op_int_roofline": (5 * cells / (k3_ms / 1e3)) / issue_peak if k3_ms > 0 else None,
+                    "stage_share": {"k1": stage["k1_oti"] / ms, "k2": k2_ms / ms, "k3": k3_ms / ms}}
+
+    # ---- CPU baseline (rank 0, N=1): bounded sample of the same pairs --------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import serra09_c as oc
+        cores = os.cpu_count() or 1
+        n_s = args.cpu_sample or max(cores, 8) * 3
+        idx = timed[np.random.default_rng(5).permutation(len(timed))[:n_s]]
+        tc0 = time.perf_counter()
+        ref_scores = oc.pairs(frames, offs, idx, oc.params(), nthreads=cores)
+        tc = time.perf_counter() - tc0
+        # parity spot check on the sample: GPU scores must equal the oracle's
+        got = eng.score_pairs(idx.astype(np.int32), params)
+        cpu = {"value": n_s / tc, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d random pairs of the timed C3 batches, %.1f s of CPU" % (n_s, tc),
+               "gcups": algorithmic_bytes(lens, idx)[0] / tc / 1e9,
+               "parity_on_sample": bool(np.array_equal(got, ref_scores))}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32+s16x2", "data": "synthetic",
+                "gcups": gcups,
+                "config": {"workload": WORKLOAD, "pairs_per_step": P, "crp_path": args.crp_path,
+                           "sharding": "pair list sharded across ranks, NCCL all_gather of score tiles" if world > 1 else "single GPU",
+                           "l2": "inputs larger than L2: each step streams >= %.1f GB of CRP scratch" % (bytes_k2 / args.steps / 1e9),
+                           "track_upload_s": setup_s},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(P * 8), "d2h_bytes_per_step": int(P * 4),
+                        "api": "acoss_b200.serra09.Serra09.similarity(idxs) -> host score matrix"},
+                "gpu_launches": int(launches),
+                "clocks": clocks, "roofline": roofline, "roofline_alu": roofline_alu, "cpu_baseline": cpu,
+                "fallback_pairs": eng.last_stats()["fallback_pairs"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -127,6 +127,12 @@ int acoss_knn_sw(acoss_ctx *ctx, const double *csms, const int64_t *offsets, con
  * fallback, [2] kernel launches, [3] cells (sum of M'*N'), [4] exact re-evaluated candidate cells. */
 int acoss_last_stats(acoss_ctx *ctx, int64_t stats[8]);
 
+/* Per-stage device timing of the pair pipeline, measured with CUDA events on the context stream:
+ * acoss_set_profiling(ctx, 1) resets and enables it; acoss_stage_ms returns the accumulated
+ * milliseconds of [0] K1 OTI, [1] K2 CRP construction, [2] K3 alignment DP, [3] reserved. */
+int acoss_set_profiling(acoss_ctx *ctx, int on);
+int acoss_stage_ms(acoss_ctx *ctx, double ms[4]);
+
 #ifdef __cplusplus
 }
 #endif
