@@ -4,6 +4,7 @@
 //   K1 oti_kernel over all pairs -> pairs are processed in fixed-pitch chunks ("slots"):
 //   K2 (fast sweep path, exact fallback) -> bit-packed CRP per slot -> K3 DP -> scores[k].
 // Nothing here computes on the CPU: without a usable device every call fails with ACOSS_E_CUDA.
+#include <math.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -38,6 +39,7 @@ struct acoss_ctx {
     int32_t n_tracks = 0;
     int32_t max_frames = 0, min_frames = 0;
     int64_t total_frames = 0;
+    int32_t fx_exp = -1000, nonneg = 0;
     int64_t ws_limit = (int64_t)24 << 30;
     // grow-only scratch
     Buf pairs, scores, oti, status, crp, rows, cols, thr_q, thr_r, rrot, aa, bb, D, halo, misc, fast, fbmap;
@@ -204,7 +206,20 @@ int acoss_set_tracks(acoss_ctx *c, const float *frames, const int64_t *offsets, 
     c->min_frames = (int32_t)mn;
     c->total_frames = total;
     TRY(launch_global_chroma(c->d_frames, c->d_offsets, n_tracks, c->d_gchroma, c->stream));
+    // feature range for the fast path's fixed point
+    TRY(ensure(c->misc, 256));
+    TRY(launch_frame_stats(c->d_frames, total, (float *)c->misc.p, c->stream));
+    float st2[2] = {0.f, 0.f};
+    CUDA_TRY(cudaMemcpyAsync(st2, c->misc.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->nonneg = (st2[1] >= 0.f) ? 1 : 0;
+    c->fx_exp = -1000;
+    if (st2[0] > 1e-30f && st2[0] < 1e30f) {
+        int e = 0;
+        frexp(2.0 * (double)st2[0] * 1.001, &e);     // 2*gmax2*1.001 = f * 2^e, f in [0.5, 1)  =>  < 2^e
+        c->fx_exp = e;
+    }
+    if (((uintptr_t)c->d_frames & 15) != 0) c->fx_exp = -1000;   // vector loads need 16 B alignment
     return ACOSS_OK;
 }
 
@@ -212,6 +227,7 @@ static TrackSet track_set(const acoss_ctx *c) {
     TrackSet ts;
     ts.frames = c->d_frames; ts.offsets = c->d_offsets; ts.gchroma = c->d_gchroma;
     ts.n_tracks = c->n_tracks; ts.max_frames = c->max_frames;
+    ts.fx_exp = c->fx_exp; ts.nonneg = c->nonneg;
     return ts;
 }
 
@@ -280,11 +296,11 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     }
     ++launches;
 
-    const bool fast = (p->crp_path == ACOSS_CRP_AUTO) && k2_fast_supported(*p, g);
+    const bool fast = (p->crp_path == ACOSS_CRP_AUTO) && k2_fast_supported(*p, g, ts);
     // bytes per slot
     const size_t exact_slot = (size_t)g.max_rows * ldd * 4 + (size_t)c->max_frames * NBINS * 4 + (size_t)(g.max_rows + g.max_cols) * 4;
     const size_t common_slot = (size_t)g.crp_words * 4 + (size_t)(g.max_rows + g.max_cols) * 4 + 8 + (size_t)2 * halo_pitch * 16;
-    const size_t fast_slot = fast ? k2_fast_slot_bytes(g) : 0;
+    const size_t fast_slot = fast ? k2_fast_slot_bytes(g, c->max_frames) : 0;
     const size_t per_slot = common_slot + (fast ? fast_slot : exact_slot);
     int64_t slots = std::max<int64_t>(1, (int64_t)(c->ws_limit / (int64_t)per_slot));
     slots = std::min<int64_t>(slots, std::min<int64_t>(K, 16384));

@@ -31,6 +31,8 @@ struct TrackSet {
     const float *gchroma;     // [n_tracks][12] global chroma: sequential f32 frame sum / max (App. A1)
     int32_t n_tracks;
     int32_t max_frames;
+    int32_t fx_exp;           // fast path fixed point: 2 * <frame, frame> < 2^fx_exp for every frame pair
+    int32_t nonneg;           // 1 when every feature value is >= 0 (HPCP); the fast path requires it
 };
 
 // Per-pair status bits written by the kernels
@@ -64,6 +66,7 @@ struct Params;   // fwd
 
 int launch_global_chroma(const float *frames, const int64_t *offsets, int n_tracks, float *gchroma,
                          cudaStream_t st);
+int launch_frame_stats(const float *frames, int64_t total_frames, float *stats2, cudaStream_t st);
 int launch_oti(const TrackSet &ts, const int32_t *pairs, int64_t n_pairs, int noti, int apply,
                int32_t *oti_out, cudaStream_t st);
 

@@ -71,6 +71,39 @@ __global__ void __launch_bounds__(256) oti_kernel(TrackSet ts, const int32_t *__
     if (live && lane == 0) oti_out[sub] = apply ? (best_s == 0x7fffffff ? 0 : best_s) : 0;
 }
 
+// max squared frame norm (as float bits: non-negative floats order like ints) and min feature value
+__global__ void __launch_bounds__(256) frame_stats_kernel(const float *__restrict__ frames, int64_t total_frames,
+                                                          float *__restrict__ stats2) {
+    float mx = 0.f, mn = 0.f;
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total_frames; f += (int64_t)gridDim.x * blockDim.x) {
+        float n2 = 0.f;
+#pragma unroll
+        for (int b = 0; b < NBINS; ++b) {
+            const float v = frames[f * NBINS + b];
+            n2 = fmaf(v, v, n2);
+            mn = fminf(mn, v);
+        }
+        mx = fmaxf(mx, n2);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax((int *)&stats2[0], __float_as_int(mx));
+        if (mn < 0.f) atomicExch((int *)&stats2[1], __float_as_int(-1.f));
+    }
+}
+
+int launch_frame_stats(const float *frames, int64_t total_frames, float *stats2, cudaStream_t st) {
+    CUDA_TRY(cudaMemsetAsync(stats2, 0, 8, st));
+    if (total_frames <= 0) return ACOSS_OK;
+    frame_stats_kernel<<<148 * 4, 256, 0, st>>>(frames, total_frames, stats2);
+    CUDA_TRY(cudaGetLastError());
+    return ACOSS_OK;
+}
+
 int launch_global_chroma(const float *frames, const int64_t *offsets, int n_tracks, float *gchroma,
                          cudaStream_t st) {
     if (n_tracks <= 0) return ACOSS_OK;

@@ -1,15 +1,696 @@
-// K2 fast path — placeholder until the sweep kernels land: reports "unsupported" so every pair
-// takes the exact path.
+// K2 (fast path) — cross-similarity, per-row / per-column k-th-nearest selection and bit-packed CRP
+// without ever writing a float distance matrix to HBM.
+//
+// Replaces essentia ChromaCrossSimilarity (call site
+// /root/reference/acoss/algorithms/rqa_serra09.py:60-66).  Results are bit-identical to the
+// reference-order arithmetic of k2_exact.cu; the structure is:
+//
+//  * The stacked squared distance is a 9-tap diagonal sum of the frame-level dot product
+//    e[a][c] = <x_a, y_c> (12 FMAs):  item(i,j) = aa_i + bb_j - 2 * sum_t e[i+t][j+t].
+//    A warp sweeps the streamed side (rows a) for a strip of owned columns c kept in REGISTERS
+//    (RC columns per lane); the diagonal sum slides: T[a][c] = T[a-1][c-1] + e[a][c] - e[a-9][c-9]
+//    (one warp shuffle for the lane boundary, one for the 9-rows-old value from the lane's
+//    neighbour's register ring).  e is quantised once to fixed point (float magic-number add), so
+//    T is an EXACT integer sliding sum: no drift, identical in every sweep and both orientations.
+//  * These approximate items z (|z - exact| <= EPS units, bound in DESIGN.md §4.2) drive two
+//    thread-private 64-bin histogram sweeps per orientation (columns: owned = reference; rows:
+//    owned = query) that bracket the order statistics floor(k), ceil(k) of every row and column
+//    to a handful of cells, and one emit sweep that writes every cell whose membership is certain
+//    and appends the few uncertain cells (inside a bracket +- 2 EPS) to per-row / per-column
+//    candidate lists.
+//  * resolve kernels recompute ONLY the candidate cells in the reference's exact operation order
+//    (float32 products, sequential float64 accumulation), pick the exact order statistics, apply
+//    essentia's percentile formula and patch the candidate bits.  Consistency checks that make
+//    the certain/uncertain split provably exact are evaluated per row/column; a pair that fails
+//    one is flagged and re-run by k2_exact.cu.
 #include "k2_fast.cuh"
 
-bool k2_fast_supported(const acoss_params &, const SlotGeom &) { return false; }
-size_t k2_fast_slot_bytes(const SlotGeom &) { return 0; }
-int launch_k2_fast(const TrackSet &, const int32_t *, const int32_t *, int64_t, int, const acoss_params &,
-                   const SlotGeom &, void *, size_t, uint32_t *, float *, float *, uint32_t *, cudaStream_t, int64_t *) {
-    acoss_set_error("fast CRP path not built");
-    return ACOSS_E_INVALID;
+namespace {
+
+constexpr int M9 = 9;               // frameStackSize handled by this path
+constexpr int HALO = M9 - 1;        // owned columns a strip recomputes (8)
+constexpr int NBIN = 64;            // histogram bins per level (+1 overflow row)
+constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
+constexpr int CAND_CAP = 32;        // candidates per row / column
+constexpr int WPC = 8;              // warps per CTA in the sweep kernels
+
+struct PairHdr {                    // per-slot header written by fast_prep_kernel
+    int32_t nq, nr, Mx, Nx;         // frames and stacked windows of query / reference
+    int32_t fk[2], ck[2];           // 0-based ranks floor(k), ceil(k): [0] rows (L = Nx), [1] columns (L = Mx)
+    int32_t quirk[2];               // 1: threshold is forced to 0 (integer k without guard, F1)
+    float kf[2];                    // fractional rank (float32, essentia arithmetic)
+    int32_t lo1, sh1;               // level-1 histogram origin / shift
+    int32_t pad[2];
+};
+
+struct FastLayout {
+    size_t slot_bytes;
+    size_t off_hdr, off_rrot, off_aaf, off_bbf, off_aai, off_bbi, off_lo, off_w, off_cb, off_sh, off_cnt,
+        off_cand, off_candd, off_rowpack;
+    int max_rows, max_cols, max_frames, lines;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+FastLayout make_layout(const SlotGeom &g, int max_frames) {
+    FastLayout L;
+    L.max_rows = g.max_rows; L.max_cols = g.max_cols; L.max_frames = max_frames;
+    L.lines = g.max_rows + g.max_cols;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 128); return r; };
+    L.off_hdr = take(sizeof(PairHdr));
+    L.off_rrot = take((size_t)(max_frames + 8) * NBINS * 4);
+    L.off_aaf = take((size_t)g.max_rows * 4);
+    L.off_bbf = take((size_t)g.max_cols * 4);
+    L.off_aai = take((size_t)g.max_rows * 4);
+    L.off_bbi = take((size_t)g.max_cols * 4);
+    L.off_lo = take((size_t)L.lines * 4);
+    L.off_w = take((size_t)L.lines * 4);
+    L.off_cb = take((size_t)L.lines * 4);
+    L.off_sh = take((size_t)L.lines * 4);
+    L.off_cnt = take((size_t)L.lines * 4);
+    L.off_cand = take((size_t)L.lines * CAND_CAP * 2);
+    L.off_candd = take((size_t)L.lines * CAND_CAP * 4);
+    L.off_rowpack = take((size_t)g.max_rows * 16);
+    L.slot_bytes = align_up(o, 256);
+    return L;
 }
-int k2_fast_collect_fallback(const uint32_t *, int64_t, int, int32_t *, int32_t *, int *count_host, cudaStream_t) {
+
+template <typename T>
+__device__ __forceinline__ T *slot_ptr(char *base, const FastLayout &L, int slot, size_t off) {
+    return reinterpret_cast<T *>(base + (size_t)slot * L.slot_bytes + off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: rotated reference copy, exact float32 norms (reference order) + their fixed-point images,
+// ranks, level-1 histogram range, zeroed candidate counters
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+                                                        const int32_t *__restrict__ oti, int64_t first,
+                                                        FastLayout L, char *__restrict__ scratch, float qperc,
+                                                        int guard, float fx_scale) {
+    __shared__ int s_max[2];
+    const int slot = blockIdx.x;
+    const int64_t k = first + slot;
+    const int q = pairs[2 * k], r = pairs[2 * k + 1], s = oti[k] % NBINS;
+    const int nq = (int)(ts.offsets[q + 1] - ts.offsets[q]), nr = (int)(ts.offsets[r + 1] - ts.offsets[r]);
+    const int Mx = nq - M9, Nx = nr - M9;
+    const float *Q = ts.frames + ts.offsets[q] * NBINS;
+    const float *R = ts.frames + ts.offsets[r] * NBINS;
+    float *rrot = slot_ptr<float>(scratch, L, slot, L.off_rrot);
+    if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
+    for (int idx = threadIdx.x; idx < (nr + 8) * NBINS; idx += blockDim.x) {
+        const int f = idx / NBINS, b = idx - f * NBINS;
+        rrot[idx] = (f < nr) ? R[f * NBINS + rot_src(b, s)] : 0.f;
+    }
+    uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
+    for (int i = threadIdx.x; i < L.lines; i += blockDim.x) cnt[i] = 0u;
+    __syncthreads();
+    float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
+    int32_t *aai = slot_ptr<int32_t>(scratch, L, slot, L.off_aai), *bbi = slot_ptr<int32_t>(scratch, L, slot, L.off_bbi);
+    int mxa = 0, mxb = 0;
+    for (int i = threadIdx.x; i < Mx + Nx; i += blockDim.x) {
+        const bool isq = i < Mx;
+        const float *src = isq ? Q + (int64_t)i * NBINS : rrot + (int64_t)(i - Mx) * NBINS;
+        double acc = 0.0;
+        for (int t = 0; t < M9; ++t) {
+            const float *fr = src + t * NBINS;
+#pragma unroll
+            for (int b = 0; b < NBINS; ++b) acc = acc_f32prod(acc, fr[b], fr[b]);
+        }
+        const float v = (float)acc;
+        const int fx = __float2int_rn(v * fx_scale);
+        if (isq) { aaf[i] = v; aai[i] = fx; mxa = max(mxa, fx); }
+        else { bbf[i - Mx] = v; bbi[i - Mx] = fx; mxb = max(mxb, fx); }
+    }
+    atomicMax(&s_max[0], mxa);
+    atomicMax(&s_max[1], mxb);
+    __syncthreads();
+    PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
+    int lo1 = -2 * EPS, sh1 = 0;
+    {
+        const long long range = (long long)s_max[0] + s_max[1] + 4 * EPS + 1;
+        while ((range >> sh1) > NBIN - 1) ++sh1;
+    }
+    int fk2[2], ck2[2], quirk2[2];
+    float kf2[2];
+    for (int o = 0; o < 2; ++o) {
+        const int Ln = (o == 0) ? Nx : Mx;                    // rows see Nx entries, columns see Mx
+        const float kf = (Ln > 1) ? __fmul_rn((float)(Ln - 1), qperc) : __fmul_rn((float)Ln, qperc);
+        const float fkf = floorf(kf), ckf = ceilf(kf);
+        kf2[o] = kf; fk2[o] = (int)fkf; ck2[o] = min((int)ckf, Ln - 1);
+        quirk2[o] = (fkf == ckf && !guard) ? 1 : 0;
+    }
+    if (threadIdx.x == 0) {
+        h->nq = nq; h->nr = nr; h->Mx = Mx; h->Nx = Nx;
+        for (int o = 0; o < 2; ++o) { h->fk[o] = fk2[o]; h->ck[o] = ck2[o]; h->quirk[o] = quirk2[o]; h->kf[o] = kf2[o]; }
+        h->lo1 = lo1; h->sh1 = sh1;
+    }
+    // level-1 bracket state for every line; emit-ready defaults for quirk sides (threshold 0)
+    int32_t *lo = slot_ptr<int32_t>(scratch, L, slot, L.off_lo), *w = slot_ptr<int32_t>(scratch, L, slot, L.off_w);
+    int32_t *cb = slot_ptr<int32_t>(scratch, L, slot, L.off_cb), *sh = slot_ptr<int32_t>(scratch, L, slot, L.off_sh);
+    int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
+    for (int i = threadIdx.x; i < L.lines; i += blockDim.x) {
+        const int side = (i < L.max_rows) ? 0 : 1;
+        if (quirk2[side]) { lo[i] = 0; w[i] = 0; cb[i] = 0; sh[i] = 0; }
+        else { lo[i] = lo1; w[i] = 0; cb[i] = 0; sh[i] = sh1; }
+    }
+    for (int i = threadIdx.x; i < Mx; i += blockDim.x) rowpack[i] = make_int4(aai[i], -2 * EPS, 4 * EPS, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the sweep: shared by the histogram kernels and the emit kernel
+// ------------------------------------------------------------------------------------------------
+template <int RC>
+struct Sweep {
+    static constexpr int COLS = 32 * RC;          // owned frames per strip
+    static constexpr int OUTW = COLS - HALO;      // output windows per strip
+    float y[RC][NBINS];                           // owned frames, pre-doubled
+    int ring[M9][RC];                             // raw bits of the last 9 quantised e values
+    int T[RC];                                    // fixed-point sliding diagonal sums (of 2e)
+    unsigned okm[RC];                             // lane has a left neighbour holding column c-9
+    unsigned nz0;                                 // all ones except on lane 0
+    float magic;
+    int mbits;
+
+    __device__ __forceinline__ void init(const float *__restrict__ Y, int nY, int cb, int lane, float magic_) {
+        magic = magic_; mbits = __float_as_int(magic_);
+        nz0 = lane ? 0xffffffffu : 0u;
+#pragma unroll
+        for (int k = 0; k < RC; ++k) {
+            const int c = cb + RC * lane + k;
+            const float4 *p = reinterpret_cast<const float4 *>(Y + (int64_t)c * NBINS);
+            float4 v0 = make_float4(0, 0, 0, 0), v1 = v0, v2 = v0;
+            if (c < nY) { v0 = __ldg(p); v1 = __ldg(p + 1); v2 = __ldg(p + 2); }
+            y[k][0] = 2.f * v0.x; y[k][1] = 2.f * v0.y; y[k][2] = 2.f * v0.z; y[k][3] = 2.f * v0.w;
+            y[k][4] = 2.f * v1.x; y[k][5] = 2.f * v1.y; y[k][6] = 2.f * v1.z; y[k][7] = 2.f * v1.w;
+            y[k][8] = 2.f * v2.x; y[k][9] = 2.f * v2.y; y[k][10] = 2.f * v2.z; y[k][11] = 2.f * v2.w;
+            T[k] = 0;
+            const int kk = ((k - M9) % RC + RC) % RC;
+            okm[k] = (lane >= (M9 - k + kk) / RC) ? 0xffffffffu : 0u;
+#pragma unroll
+            for (int u = 0; u < M9; ++u) ring[u][k] = mbits;
+        }
+    }
+
+    // one streamed frame (12 floats in three float4): updates T for the lane's RC columns.
+    // U = a % 9 (static ring slot).
+    template <int U>
+    __device__ __forceinline__ void row(const float4 &x0, const float4 &x1, const float4 &x2) {
+        int eb[RC], old[RC];
+#pragma unroll
+        for (int k = 0; k < RC; ++k) {
+            float acc = __fmul_rn(x0.x, y[k][0]);
+            acc = __fmaf_rn(x0.y, y[k][1], acc); acc = __fmaf_rn(x0.z, y[k][2], acc); acc = __fmaf_rn(x0.w, y[k][3], acc);
+            acc = __fmaf_rn(x1.x, y[k][4], acc); acc = __fmaf_rn(x1.y, y[k][5], acc); acc = __fmaf_rn(x1.z, y[k][6], acc);
+            acc = __fmaf_rn(x1.w, y[k][7], acc); acc = __fmaf_rn(x2.x, y[k][8], acc); acc = __fmaf_rn(x2.y, y[k][9], acc);
+            acc = __fmaf_rn(x2.z, y[k][10], acc); acc = __fmaf_rn(x2.w, y[k][11], acc);
+            eb[k] = __float_as_int(__fadd_rn(acc, magic));
+        }
+        // e[a-9][c-9]: column c-9 lives dl lanes to the left, in register (k - 9) mod RC of ring slot U
+#pragma unroll
+        for (int k = 0; k < RC; ++k) {
+            const int kk = ((k - M9) % RC + RC) % RC;
+            const int dl = (M9 - k + kk) / RC;
+            const unsigned v = (unsigned)__shfl_up_sync(0xffffffffu, ring[U][kk], dl);
+            old[k] = (int)((v & okm[k]) | ((unsigned)mbits & ~okm[k]));
+        }
+        const int tl = (int)((unsigned)__shfl_up_sync(0xffffffffu, T[RC - 1], 1) & nz0);
+#pragma unroll
+        for (int k = RC - 1; k >= 1; --k) T[k] = T[k - 1] + eb[k] - old[k];
+        T[0] = tl + eb[0] - old[0];
+#pragma unroll
+        for (int k = 0; k < RC; ++k) ring[U][k] = eb[k];
+    }
+};
+
+template <int V> struct IC { static constexpr int value = V; };
+template <bool V> struct BC { static constexpr bool value = V; };
+
+// Drives a sweep over streamed frames 0 .. nrows-1 (nrows >= 10 always: Mx >= 2).  The next frame and
+// the next row's parameter word are prefetched into registers one row ahead.  fn(a, param) runs for
+// rows a >= HALO, param = P[a - HALO].
+template <int RC, typename PT, typename Fn>
+__device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict__ X, const PT *__restrict__ P,
+                                          int nrows, Fn &&fn) {
+    const float4 *px = reinterpret_cast<const float4 *>(X);
+    float4 c0 = __ldg(px), c1 = __ldg(px + 1), c2 = __ldg(px + 2);
+    PT pc{};
+    const PT *pp = P - HALO;                       // pp[a] is the parameter of row a
+    int a = 0;
+    auto step = [&](auto uc, auto callc, auto pfc) {
+        constexpr int U = decltype(uc)::value;
+        constexpr bool CALL = decltype(callc)::value, PF = decltype(pfc)::value;
+        px += 3;
+        const float4 n0 = __ldg(px), n1 = __ldg(px + 1), n2 = __ldg(px + 2);
+        PT pn{};
+        if (PF) pn = __ldg(pp + a + 1);
+        sw.template row<U>(c0, c1, c2);
+        if (CALL) fn(a, pc);
+        ++a;
+        c0 = n0; c1 = n1; c2 = n2;
+        if (PF) pc = pn;
+    };
+    // rows 0..8: the diagonal sums fill up; only row 8 produces a window
+    step(IC<0>{}, BC<false>{}, BC<false>{}); step(IC<1>{}, BC<false>{}, BC<false>{}); step(IC<2>{}, BC<false>{}, BC<false>{});
+    step(IC<3>{}, BC<false>{}, BC<false>{}); step(IC<4>{}, BC<false>{}, BC<false>{}); step(IC<5>{}, BC<false>{}, BC<false>{});
+    step(IC<6>{}, BC<false>{}, BC<false>{}); step(IC<7>{}, BC<false>{}, BC<true>{}); step(IC<8>{}, BC<true>{}, BC<true>{});
+#pragma unroll 1
+    while (a + M9 <= nrows) {
+        step(IC<0>{}, BC<true>{}, BC<true>{}); step(IC<1>{}, BC<true>{}, BC<true>{}); step(IC<2>{}, BC<true>{}, BC<true>{});
+        step(IC<3>{}, BC<true>{}, BC<true>{}); step(IC<4>{}, BC<true>{}, BC<true>{}); step(IC<5>{}, BC<true>{}, BC<true>{});
+        step(IC<6>{}, BC<true>{}, BC<true>{}); step(IC<7>{}, BC<true>{}, BC<true>{}); step(IC<8>{}, BC<true>{}, BC<true>{});
+    }
+    const int rem = nrows - a;                     // 0..8 rows left, ring slots 0..rem-1
+    if (rem > 0) step(IC<0>{}, BC<true>{}, BC<true>{});
+    if (rem > 1) step(IC<1>{}, BC<true>{}, BC<true>{});
+    if (rem > 2) step(IC<2>{}, BC<true>{}, BC<true>{});
+    if (rem > 3) step(IC<3>{}, BC<true>{}, BC<true>{});
+    if (rem > 4) step(IC<4>{}, BC<true>{}, BC<true>{});
+    if (rem > 5) step(IC<5>{}, BC<true>{}, BC<true>{});
+    if (rem > 6) step(IC<6>{}, BC<true>{}, BC<true>{});
+    if (rem > 7) step(IC<7>{}, BC<true>{}, BC<true>{});
+}
+
+// ------------------------------------------------------------------------------------------------
+// histogram sweep.  ORIENT = 0: owned = reference columns (column thresholds), streamed = query.
+//                   ORIENT = 1: owned = query rows (row thresholds), streamed = rotated reference.
+// LEVEL = 1: coarse bins over the whole pair range -> per-line refined origin / shift.
+// LEVEL = 2: fine bins -> final bracket [lo, lo + w) holding ranks floor(k) and ceil(k).
+// ------------------------------------------------------------------------------------------------
+template <int RC, int ORIENT, int LEVEL>
+__global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+                                                             int64_t first, int n, FastLayout L,
+                                                             char *__restrict__ scratch, int strips_max, float magic,
+                                                             uint32_t *__restrict__ status) {
+    extern __shared__ uint32_t s_hist[];                      // [WPC][NBIN + 1][32], two 16-bit counters per word
+    using SW = Sweep<RC>;
+    static_assert(RC == 2, "histogram packing is written for RC == 2");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t task = (int64_t)blockIdx.x * WPC + warp;
+    const int slot = (int)(task / strips_max), strip = (int)(task % strips_max);
+    if (slot >= n) return;
+    const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
+    if (h->quirk[ORIENT == 0 ? 1 : 0]) return;               // threshold forced to 0: nothing to select
+    const int64_t k = first + slot;
+    const int q = pairs[2 * k];
+    const int nY = (ORIENT == 0) ? h->nr : h->nq, nX = (ORIENT == 0) ? h->nq : h->nr;
+    const int My = nY - M9;                                   // owned windows
+    const int cb = strip * SW::OUTW;
+    if (cb >= My) return;
+    const float *Qf = ts.frames + ts.offsets[q] * NBINS;
+    const float *Rf = slot_ptr<float>(scratch, L, slot, L.off_rrot);
+    const float *Y = (ORIENT == 0) ? Rf : Qf, *X = (ORIENT == 0) ? Qf : Rf;
+    const int32_t *xn = slot_ptr<int32_t>(scratch, L, slot, ORIENT == 0 ? L.off_aai : L.off_bbi);
+    const int32_t *yn = slot_ptr<int32_t>(scratch, L, slot, ORIENT == 0 ? L.off_bbi : L.off_aai);
+    const int line0 = (ORIENT == 0) ? L.max_rows : 0;         // first line index of the owned side
+    int32_t *lo_a = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + line0;
+    int32_t *w_a = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + line0;
+    int32_t *cb_a = slot_ptr<int32_t>(scratch, L, slot, L.off_cb) + line0;
+    int32_t *sh_a = slot_ptr<int32_t>(scratch, L, slot, L.off_sh) + line0;
+
+    SW sw;
+    sw.init(Y, nY, cb, lane, magic);
+    int ynrel[RC], shf[RC];
+    bool valid[RC];
+#pragma unroll
+    for (int kk = 0; kk < RC; ++kk) {
+        const int j = cb + RC * lane + kk - HALO;            // owned window of this register column
+        valid[kk] = (j >= cb) && (j < My) && (j < cb + SW::OUTW);
+        ynrel[kk] = valid[kk] ? yn[j] - lo_a[j] : 0x40000000;  // invalid columns land in the overflow bin
+        shf[kk] = valid[kk] ? sh_a[j] : 0;
+    }
+    uint32_t *hist = s_hist + (size_t)warp * (NBIN + 1) * 32 + lane;
+#pragma unroll 1
+    for (int b = 0; b <= NBIN; ++b) hist[b * 32] = 0u;
+    __syncwarp();
+
+    const int nrows = nX - 1;                                 // streamed frames 0 .. nX-2 (F4: last frame unused)
+    run_sweep<RC, int>(sw, X, xn, nrows, [&](int, int xb) {
+#pragma unroll
+        for (int kk = 0; kk < RC; ++kk) {
+            const unsigned zr = (unsigned)(xb + ynrel[kk] - sw.T[kk]);
+            const unsigned idx = min(zr >> shf[kk], (unsigned)NBIN);
+            hist[idx * 32] += 1u << (16 * kk);
+        }
+    });
+    __syncwarp();
+    // per-thread scan of its own columns' histograms
+    const int fk = h->fk[ORIENT == 0 ? 1 : 0], ck = h->ck[ORIENT == 0 ? 1 : 0];
+#pragma unroll
+    for (int kk = 0; kk < RC; ++kk) {
+        if (!valid[kk]) continue;
+        const int j = cb + RC * lane + kk - HALO;
+        const uint32_t *hp = hist;
+        const int hs = 16 * kk;
+        const int base = cb_a[j];                             // items below lo (from the previous level)
+        int cum = base, b1 = -1, b2 = -1, cb1 = 0, cend = 0;
+        for (int b = 0; b < NBIN; ++b) {
+            const int c = (hp[b * 32] >> hs) & 0xffff;
+            if (b1 < 0 && cum + c > fk) { b1 = b; cb1 = cum; }
+            if (b2 < 0 && cum + c > ck) { b2 = b; cend = cum + c; }
+            cum += c;
+        }
+        const int sh = shf[kk], lo = lo_a[j];
+        if (b1 < 0 || b2 < 0) {                               // ranks not inside the binned range
+            atomicOr(&status[k], PAIR_ST_FALLBACK);
+            continue;
+        }
+        if (LEVEL == 1) {
+            const long long range = (long long)(b2 - b1 + 1) << sh;
+            int sh2 = 0;
+            while ((range >> sh2) > NBIN) ++sh2;
+            lo_a[j] = lo + (b1 << sh);
+            sh_a[j] = sh2;
+            cb_a[j] = cb1;
+        } else {
+            lo_a[j] = lo + (b1 << sh);
+            w_a[j] = (b2 - b1 + 1) << sh;
+            cb_a[j] = cb1;
+            if (cend - cb1 > CAND_CAP - 8) atomicOr(&status[k], PAIR_ST_FALLBACK);   // bracket too crowded (ties)
+            if (ORIENT == 1) {
+                int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
+                rowpack[j] = make_int4(yn[j], lo + (b1 << sh) - 2 * EPS, ((b2 - b1 + 1) << sh) + 4 * EPS, 0);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// emit sweep (orientation 0: owned = reference columns, streamed = query rows)
+// ------------------------------------------------------------------------------------------------
+template <int RC>
+__global__ void __launch_bounds__(32 * WPC, 2) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+                                                             int64_t first, int n, FastLayout L,
+                                                             char *__restrict__ scratch, int strips_max, float magic,
+                                                             uint32_t *__restrict__ crp_all, int words,
+                                                             int64_t crp_words) {
+    using SW = Sweep<RC>;
+    static_assert(RC == 2, "emit word assembly is written for RC == 2");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t task = (int64_t)blockIdx.x * WPC + warp;
+    const int slot = (int)(task / strips_max), strip = (int)(task % strips_max);
+    if (slot >= n) return;
+    const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
+    const int64_t k = first + slot;
+    const int q = pairs[2 * k];
+    const int nY = h->nr, nX = h->nq, My = nY - M9, Mx = nX - M9;
+    const int cb = strip * SW::OUTW;
+    if (cb >= My) return;
+    const float *X = ts.frames + ts.offsets[q] * NBINS;
+    const float *Y = slot_ptr<float>(scratch, L, slot, L.off_rrot);
+    const int32_t *yn = slot_ptr<int32_t>(scratch, L, slot, L.off_bbi);
+    const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
+    const int32_t *lo_c = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + L.max_rows;
+    const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
+    uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
+    uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
+    uint32_t *crp = crp_all + (int64_t)slot * crp_words;
+
+    SW sw;
+    sw.init(Y, nY, cb, lane, magic);
+    int ynv[RC], clo2[RC];
+    unsigned cw2[RC];
+    int jcol[RC];
+#pragma unroll
+    for (int kk = 0; kk < RC; ++kk) {
+        const int j = cb + RC * lane + kk - HALO;
+        const bool valid = (j >= cb) && (j < My) && (j < cb + SW::OUTW);
+        jcol[kk] = j;
+        ynv[kk] = valid ? yn[j] : 0;
+        clo2[kk] = valid ? lo_c[j] - 2 * EPS : -0x40000000;  // invalid: never "in", never a candidate
+        cw2[kk] = valid ? (unsigned)(w_c[j] + 4 * EPS) : 0u;
+    }
+    // output placement: strip bits t = 0..OUTW-1 <-> CRP columns cb + t
+    const int wlo = cb >> 5, bsh = cb & 31;
+    const int nrows = nX - 1;
+    run_sweep<RC, int4>(sw, X, rowpack, nrows, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
+        const int i = a - HALO;                               // query window (CRP row); i < Mx by construction
+        unsigned nib = 0u;
+        bool rz[RC], cz[RC];
+        int dr[RC], dc[RC];
+        bool anyc = false;
+#pragma unroll
+        for (int kk = 0; kk < RC; ++kk) {
+            const int z = rp.x + ynv[kk] - sw.T[kk];
+            dr[kk] = z - rp.y;
+            dc[kk] = z - clo2[kk];
+            // cells with a (near-)zero squared distance always go through the exact evaluation, so a
+            // negative exact item (NaN distance, F7) is detected exactly like in the reference order
+            const bool zz = (z < 2 * EPS) && cw2[kk] != 0u;
+            const bool in = ((dr[kk] & dc[kk]) < 0) && !zz;   // below both certain-in limits
+            rz[kk] = (((unsigned)dr[kk] < (unsigned)rp.z) && cw2[kk] != 0u) || zz;
+            cz[kk] = (unsigned)dc[kk] < cw2[kk];
+            nib |= in ? (1u << kk) : 0u;
+            anyc |= rz[kk] | cz[kk];
+        }
+        // the lane's RC bits sit at strip bit RC*lane - HALO; assemble the 64-bit strip pattern
+        const int pos = RC * lane - HALO;                     // may be negative for halo lanes (nib == 0 there)
+        unsigned long long pat = (pos >= 0) ? ((unsigned long long)nib << pos) : 0ull;
+        unsigned p0 = __reduce_or_sync(0xffffffffu, (unsigned)pat);
+        unsigned p1 = __reduce_or_sync(0xffffffffu, (unsigned)(pat >> 32));
+        if (lane == 0) {
+            const unsigned long long P = ((unsigned long long)p1 << 32) | p0;   // bits 0..55
+            uint32_t *rowp = crp + (int64_t)i * words + wlo;
+            const unsigned w0 = (unsigned)(P << bsh);
+            const unsigned w1 = (unsigned)((bsh ? (P >> (32 - bsh)) : (P >> 32)));
+            const unsigned w2 = bsh ? (unsigned)(P >> (64 - bsh)) : 0u;
+            if (w0) atomicOr(rowp, w0);
+            if (w1) atomicOr(rowp + 1, w1);
+            if (w2) atomicOr(rowp + 2, w2);
+        }
+        if (__any_sync(0xffffffffu, anyc)) {
+#pragma unroll
+            for (int kk = 0; kk < RC; ++kk) {
+                if (rz[kk]) {
+                    const unsigned p = atomicAdd(&cnt[i], 1u);
+                    if (p < CAND_CAP) cand[(size_t)i * CAND_CAP + p] = (uint16_t)(jcol[kk] | (dr[kk] < 2 * EPS ? 0x8000 : 0));
+                    // (zero-zone cells far below the bracket have dr < 0 < 2 EPS: counted as "below", consistent with cb)
+                }
+                if (cz[kk]) {
+                    const int line = L.max_rows + jcol[kk];
+                    const unsigned p = atomicAdd(&cnt[line], 1u);
+                    if (p < CAND_CAP) cand[(size_t)line * CAND_CAP + p] = (uint16_t)(i | (dc[kk] < 2 * EPS ? 0x8000 : 0));
+                }
+            }
+        }
+    });
+    (void)Mx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resolve: exact re-evaluation of candidate cells, exact order statistics, thresholds, bit patch
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float exact_item(const float *__restrict__ Q, const float *__restrict__ R, int i, int j,
+                                            float aa, float bb) {
+    const float *a = Q + (int64_t)i * NBINS, *b = R + (int64_t)j * NBINS;     // 9 consecutive frames each
+    double acc = 0.0;
+#pragma unroll 4
+    for (int t = 0; t < M9 * NBINS; ++t) acc = acc_f32prod(acc, a[t], b[t]);
+    return __fadd_rn(__fsub_rn(aa, __fmul_rn(2.f, (float)acc)), bb);
+}
+
+// one 8-lane group per line (row or column)
+__global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+                                                               int64_t first, int n, FastLayout L,
+                                                               char *__restrict__ scratch, int guard, double unit,
+                                                               float *__restrict__ thr_q_all,
+                                                               float *__restrict__ thr_r_all,
+                                                               uint32_t *__restrict__ status) {
+    __shared__ float s_item[32][CAND_CAP];
+    __shared__ float s_sel[32][4];
+    const int slot = blockIdx.y;
+    if (slot >= n) return;
+    const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    const int gline = blockIdx.x * 32 + grp;                  // 0 .. Mx+Nx-1 (rows then columns)
+    const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
+    const int Mx = h->Mx, Nx = h->Nx;
+    const bool live = gline < Mx + Nx;
+    const bool isrow = gline < Mx;
+    const int idx = isrow ? gline : gline - Mx;
+    const int line = isrow ? idx : L.max_rows + idx;
+    const int64_t k = first + slot;
+    const int q = pairs[2 * k];
+    const float *Q = ts.frames + ts.offsets[q] * NBINS;
+    const float *R = slot_ptr<float>(scratch, L, slot, L.off_rrot);
+    const float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
+    const uint32_t *cnt_a = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
+    const uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
+    float *candd = slot_ptr<float>(scratch, L, slot, L.off_candd);
+    const unsigned gmask = 0xffu << (8 * ((threadIdx.x & 31) >> 3));
+    int cnt = 0;
+    bool over = false;
+    if (live) {
+        const unsigned c = cnt_a[line];
+        over = c > CAND_CAP;
+        cnt = (int)min(c, (unsigned)CAND_CAP);
+    }
+    int nbelow = 0;
+    bool nan = false;
+    for (int p = sub; p < cnt; p += 8) {
+        const unsigned e = cand[(size_t)line * CAND_CAP + p];
+        const int other = e & 0x7fff;
+        const int i = isrow ? idx : other, j = isrow ? other : idx;
+        const float item = exact_item(Q, R, i, j, aaf[i], bbf[j]);
+        const float d = __fsqrt_rn(item);
+        nan |= (d != d);
+        candd[(size_t)line * CAND_CAP + p] = d;
+        s_item[grp][p] = item;
+        nbelow += (e >> 15) & 1;
+    }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) nbelow += __shfl_xor_sync(gmask, nbelow, o, 8);
+    __syncwarp(gmask);
+    if (!live) return;
+    if (nan) atomicOr(&status[k], PAIR_ST_NAN);
+    const int side = isrow ? 0 : 1;
+    const int fk = h->fk[side], ck = h->ck[side];
+    const int32_t lo = slot_ptr<int32_t>(scratch, L, slot, L.off_lo)[line];
+    const int32_t w = slot_ptr<int32_t>(scratch, L, slot, L.off_w)[line];
+    const int c0 = slot_ptr<int32_t>(scratch, L, slot, L.off_cb)[line] - nbelow;   // items below every candidate
+    const int rfk = fk - c0, rck = ck - c0;
+    bool bad = over;
+    float thr = 0.f;
+    if (!h->quirk[side]) {
+        if (rfk < 0 || rck >= cnt || rfk > rck) bad = true;
+        // rank by counting (cnt <= 32): the candidate whose rank is rfk / rck publishes its item
+        for (int p = sub; p < cnt; p += 8) {
+            const float v = s_item[grp][p];
+            int rank = 0;
+            for (int p2 = 0; p2 < cnt; ++p2) {
+                const float v2 = s_item[grp][p2];
+                rank += (v2 < v) || (v2 == v && p2 < p);
+            }
+            if (rank == rfk) s_sel[grp][0] = v;
+            if (rank == rck) s_sel[grp][1] = v;
+        }
+        __syncwarp(gmask);
+        if (!bad) {
+            const float ifk = s_sel[grp][0], ick = s_sel[grp][1];
+            // every excluded cell below the candidate zone has exact item < (lo - EPS) units, every excluded cell
+            // above it has exact item >= (lo + w + EPS) units: the selected order statistics must sit between
+            const double lo_e = (double)(lo - EPS) * unit, hi_e = (double)(lo + w + EPS) * unit;
+            if ((double)ifk < lo_e || (double)ick >= hi_e) bad = true;
+            const float sfk = __fsqrt_rn(ifk), sck = __fsqrt_rn(ick);
+            const float kf = h->kf[side];
+            const float fkf = floorf(kf), ckf = ceilf(kf);
+            if (guard && fkf == ckf) thr = sfk;
+            else thr = __fadd_rn(__fmul_rn(sfk, __fsub_rn(ckf, kf)), __fmul_rn(sck, __fsub_rn(kf, fkf)));
+            // cells emitted as certainly-in have exact item < (lo - EPS): their d must be <= thr;
+            // cells dropped as certainly-out have exact item >= (lo + w + EPS): their d must be > thr
+            const double t2 = (double)thr * (double)thr;
+            if (lo_e > 0.0 && t2 < lo_e * (1.0 + 1e-6)) bad = true;
+            if (t2 >= hi_e * (1.0 - 1e-6)) bad = true;
+        }
+    }
+    if (sub == 0) {
+        if (bad) atomicOr(&status[k], PAIR_ST_FALLBACK);
+        if (isrow) thr_q_all[(int64_t)slot * L.max_rows + idx] = thr;
+        else thr_r_all[(int64_t)slot * L.max_cols + idx] = thr;
+    }
+}
+
+__global__ void __launch_bounds__(256) fast_resolve_bits_kernel(int n, FastLayout L, char *__restrict__ scratch,
+                                                                const float *__restrict__ thr_q_all,
+                                                                const float *__restrict__ thr_r_all,
+                                                                uint32_t *__restrict__ crp_all, int words,
+                                                                int64_t crp_words) {
+    const int slot = blockIdx.y;
+    if (slot >= n) return;
+    const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
+    const int Mx = h->Mx, Nx = h->Nx;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;      // (line, position)
+    const int gline = t / CAND_CAP, p = t % CAND_CAP;
+    if (gline >= Mx + Nx) return;
+    const bool isrow = gline < Mx;
+    const int idx = isrow ? gline : gline - Mx;
+    const int line = isrow ? idx : L.max_rows + idx;
+    const uint32_t cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt)[line];
+    if ((unsigned)p >= min(cnt, (unsigned)CAND_CAP)) return;
+    const unsigned e = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand)[(size_t)line * CAND_CAP + p];
+    const float d = slot_ptr<float>(scratch, L, slot, L.off_candd)[(size_t)line * CAND_CAP + p];
+    const int other = e & 0x7fff;
+    const int i = isrow ? idx : other, j = isrow ? other : idx;
+    const float tq = thr_q_all[(int64_t)slot * L.max_rows + i], tr = thr_r_all[(int64_t)slot * L.max_cols + j];
+    if ((__fsub_rn(tq, d) >= 0.f) && (__fsub_rn(tr, d) >= 0.f))
+        atomicOr(crp_all + (int64_t)slot * crp_words + (int64_t)i * words + (j >> 5), 1u << (j & 31));
+}
+
+__global__ void collect_fallback_kernel(const uint32_t *__restrict__ status, int64_t first, int n,
+                                        int32_t *__restrict__ map, int32_t *__restrict__ count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    if (status[first + t] & PAIR_ST_FALLBACK) map[atomicAdd(count, 1)] = (int32_t)(first + t);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+bool k2_fast_supported(const acoss_params &p, const SlotGeom &g, const TrackSet &ts) {
+    return p.m == M9 && p.tau == 1 && ts.fx_exp > -100 && ts.nonneg && g.max_rows < 16000 && g.max_cols < 16000 &&
+           g.max_rows >= 2 && g.max_cols >= 2;
+}
+
+size_t k2_fast_slot_bytes(const SlotGeom &g, int max_frames) { return make_layout(g, max_frames).slot_bytes; }
+
+int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti, int64_t first, int n,
+                   const acoss_params &p, const SlotGeom &g, void *scratch, size_t slot_bytes, uint32_t *crp,
+                   float *thr_q, float *thr_r, uint32_t *status, cudaStream_t st, int64_t *launches) {
+    if (n <= 0) return ACOSS_OK;
+    constexpr int RC = 2;
+    const FastLayout L = make_layout(g, ts.max_frames);
+    if (L.slot_bytes != slot_bytes) { acoss_set_error("fast path: scratch layout mismatch"); return ACOSS_E_INVALID; }
+    char *base = (char *)scratch;
+    const float qperc = (float)((double)(p.kappa * 100.f) / 100.);
+    // fixed point: 2e < 2^fx_exp, unit = 2^(fx_exp - 23); magic = 2^fx_exp puts 2e in one binade
+    const float magic = ldexpf(1.f, ts.fx_exp);
+    const double unit = ldexp(1.0, ts.fx_exp - 23);
+    const float fx_scale = ldexpf(1.f, 23 - ts.fx_exp);
+    CUDA_TRY(cudaMemsetAsync(crp, 0, (size_t)n * g.crp_words * 4, st));
+    fast_prep_kernel<<<n, 256, 0, st>>>(ts, pairs, oti, first, L, base, qperc, p.integer_guard, fx_scale);
+    CUDA_TRY(cudaGetLastError());
+    const int outw = Sweep<RC>::OUTW;
+    const int strips_c = (g.max_cols + outw - 1) / outw, strips_r = (g.max_rows + outw - 1) / outw;
+    const size_t smem = (size_t)WPC * (NBIN + 1) * 32 * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const unsigned gc = (unsigned)(((int64_t)n * strips_c + WPC - 1) / WPC), gr = (unsigned)(((int64_t)n * strips_r + WPC - 1) / WPC);
+    fast_hist_kernel<RC, 0, 1><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status);
+    fast_hist_kernel<RC, 0, 2><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status);
+    fast_hist_kernel<RC, 1, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status);
+    fast_hist_kernel<RC, 1, 2><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status);
+    CUDA_TRY(cudaGetLastError());
+    fast_emit_kernel<RC><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
+    CUDA_TRY(cudaGetLastError());
+    const int lines = g.max_rows + g.max_cols;
+    fast_resolve_thr_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(ts, pairs, first, n, L, base, p.integer_guard, unit,
+                                                                       thr_q, thr_r, status);
+    CUDA_TRY(cudaGetLastError());
+    fast_resolve_bits_kernel<<<dim3((lines * CAND_CAP + 255) / 256, n), 256, 0, st>>>(n, L, base, thr_q, thr_r, crp, g.words,
+                                                                                      g.crp_words);
+    CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 9;
+    return ACOSS_OK;
+}
+
+int k2_fast_collect_fallback(const uint32_t *status, int64_t first, int n, int32_t *map_dev, int32_t *count_dev,
+                             int *count_host, cudaStream_t st) {
     *count_host = 0;
+    if (n <= 0) return ACOSS_OK;
+    CUDA_TRY(cudaMemsetAsync(count_dev, 0, 4, st));
+    collect_fallback_kernel<<<(n + 255) / 256, 256, 0, st>>>(status, first, n, map_dev, count_dev);
+    CUDA_TRY(cudaGetLastError());
+    int32_t c = 0;
+    CUDA_TRY(cudaMemcpyAsync(&c, count_dev, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *count_host = c;
     return ACOSS_OK;
 }

@@ -3,9 +3,9 @@
 #include "common.cuh"
 
 // true when the sweep kernels can handle these parameters (tau == 1, m <= 16, sizes in range)
-bool k2_fast_supported(const acoss_params &p, const SlotGeom &g);
+bool k2_fast_supported(const acoss_params &p, const SlotGeom &g, const TrackSet &ts);
 // scratch bytes per slot for the fast path
-size_t k2_fast_slot_bytes(const SlotGeom &g);
+size_t k2_fast_slot_bytes(const SlotGeom &g, int max_frames);
 // CRP bits + exact thresholds for pairs[first..first+n); pairs that fail a consistency check get
 // PAIR_ST_FALLBACK in status[k] and are re-run by the exact path
 int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti, int64_t first, int n,
