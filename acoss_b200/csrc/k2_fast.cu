@@ -32,7 +32,8 @@ constexpr int HALO = M9 - 1;        // owned columns a strip recomputes (8)
 constexpr int NBIN = 64;            // histogram bins per level (+1 overflow row)
 constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
 constexpr int CAND_CAP = 32;        // candidates per row / column
-constexpr int WPC = 8;              // warps per CTA in the sweep kernels
+constexpr int WPC = 4;              // warps per CTA in the sweep kernels
+constexpr int SLIST_CAP = 2048;     // uncertain cells one emit strip may record before the pair is flagged
 
 struct PairHdr {                    // per-slot header written by fast_prep_kernel
     int32_t nq, nr, Mx, Nx;         // frames and stacked windows of query / reference
@@ -46,8 +47,8 @@ struct PairHdr {                    // per-slot header written by fast_prep_kern
 struct FastLayout {
     size_t slot_bytes;
     size_t off_hdr, off_rrot, off_aaf, off_bbf, off_aai, off_bbi, off_lo, off_w, off_cb, off_sh, off_cnt,
-        off_cand, off_candd, off_rowpack;
-    int max_rows, max_cols, max_frames, lines;
+        off_cand, off_candd, off_rowpack, off_slist, off_scnt;
+    int max_rows, max_cols, max_frames, lines, strips_c;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -72,6 +73,9 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.off_cand = take((size_t)L.lines * CAND_CAP * 2);
     L.off_candd = take((size_t)L.lines * CAND_CAP * 4);
     L.off_rowpack = take((size_t)g.max_rows * 16);
+    L.strips_c = (g.max_cols + (32 * 2 - HALO) - 1) / (32 * 2 - HALO);
+    L.off_slist = take((size_t)L.strips_c * SLIST_CAP * 4);
+    L.off_scnt = take((size_t)L.strips_c * 4);
     L.slot_bytes = align_up(o, 256);
     return L;
 }
@@ -105,6 +109,7 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
     }
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     for (int i = threadIdx.x; i < L.lines; i += blockDim.x) cnt[i] = 0u;
+    for (int i = threadIdx.x; i < L.strips_c; i += blockDim.x) slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[i] = 0u;
     __syncthreads();
     float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
     int32_t *aai = slot_ptr<int32_t>(scratch, L, slot, L.off_aai), *bbi = slot_ptr<int32_t>(scratch, L, slot, L.off_bbi);
@@ -279,7 +284,7 @@ __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict
 // LEVEL = 2: fine bins -> final bracket [lo, lo + w) holding ranks floor(k) and ceil(k).
 // ------------------------------------------------------------------------------------------------
 template <int RC, int ORIENT, int LEVEL>
-__global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+__global__ void __launch_bounds__(32 * WPC, 5) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
                                                              uint32_t *__restrict__ status) {
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
         for (int kk = 0; kk < RC; ++kk) {
             const unsigned zr = (unsigned)(xb + ynrel[kk] - sw.T[kk]);
             const unsigned idx = min(zr >> shf[kk], (unsigned)NBIN);
-            hist[idx * 32] += 1u << (16 * kk);
+            atomicAdd(&hist[idx * 32], 1u << (16 * kk));   // thread-private bank: conflict-free shared atomic
         }
     });
     __syncwarp();
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
 // emit sweep (orientation 0: owned = reference columns, streamed = query rows)
 // ------------------------------------------------------------------------------------------------
 template <int RC>
-__global__ void __launch_bounds__(32 * WPC, 2) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+__global__ void __launch_bounds__(32 * WPC, 4) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
                                                              uint32_t *__restrict__ crp_all, int words,
@@ -403,79 +408,110 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_emit_kernel(TrackSet ts, con
     const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
     const int32_t *lo_c = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + L.max_rows;
     const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
-    uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
-    uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
+    uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * SLIST_CAP;
+    unsigned nlist = 0u;
+    const unsigned ltmask = (1u << lane) - 1u;
     uint32_t *crp = crp_all + (int64_t)slot * crp_words;
 
     SW sw;
     sw.init(Y, nY, cb, lane, magic);
-    int ynv[RC], clo2[RC];
-    unsigned cw2[RC];
+    int ynv[RC], ycl[RC];                                     // bb_fix[j] and bb_fix[j] - (colLo - 2 EPS)
+    unsigned cw2[RC];                                         // colW + 4 EPS (0 for columns this lane does not emit)
     int jcol[RC];
 #pragma unroll
     for (int kk = 0; kk < RC; ++kk) {
         const int j = cb + RC * lane + kk - HALO;
         const bool valid = (j >= cb) && (j < My) && (j < cb + SW::OUTW);
         jcol[kk] = j;
-        ynv[kk] = valid ? yn[j] : 0;
-        clo2[kk] = valid ? lo_c[j] - 2 * EPS : -0x40000000;  // invalid: never "in", never a candidate
+        ynv[kk] = valid ? yn[j] : 0x20000000;                 // invalid: z huge => never in, never near zero
+        ycl[kk] = valid ? yn[j] - (lo_c[j] - 2 * EPS) : 0x20000000;
         cw2[kk] = valid ? (unsigned)(w_c[j] + 4 * EPS) : 0u;
     }
-    // output placement: strip bits t = 0..OUTW-1 <-> CRP columns cb + t
-    const int wlo = cb >> 5, bsh = cb & 31;
+    // output placement: strip bit t = RC*lane + kk - HALO <-> CRP column cb + t.  cb is a multiple of 8 and the
+    // lane's RC = 2 bits start at an even position, so they never straddle a 32-bit word: every lane
+    // contributes its bits to word lword of the row at a position that is constant over the sweep.
+    const int gpos = (cb & 31) + RC * lane - HALO;
+    const int lword = gpos >> 5;                              // -1 for halo lanes (they contribute nothing)
+    const unsigned bit0 = (lword >= 0) ? (1u << (gpos & 31)) : 0u, bit1 = bit0 << 1;
+    const unsigned sel0 = lword == 0 ? 0xffffffffu : 0u, sel1 = lword == 1 ? 0xffffffffu : 0u, sel2 = lword == 2 ? 0xffffffffu : 0u;
+    const unsigned full = __activemask();                     // all 32 lanes (kept in a register)
+    uint32_t *rowp = crp + (cb >> 5) + ((lane < 3) ? lane : 0);   // advances by `words` per row
     const int nrows = nX - 1;
     run_sweep<RC, int4>(sw, X, rowpack, nrows, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
-        const int i = a - HALO;                               // query window (CRP row); i < Mx by construction
-        unsigned nib = 0u;
-        bool rz[RC], cz[RC];
+        const int rb = rp.x - rp.y;                           // dr = z - (rowLo - 2 EPS) = rb + bb - T
         int dr[RC], dc[RC];
+        unsigned v = 0u;
         bool anyc = false;
 #pragma unroll
         for (int kk = 0; kk < RC; ++kk) {
             const int z = rp.x + ynv[kk] - sw.T[kk];
-            dr[kk] = z - rp.y;
-            dc[kk] = z - clo2[kk];
-            // cells with a (near-)zero squared distance always go through the exact evaluation, so a
-            // negative exact item (NaN distance, F7) is detected exactly like in the reference order
-            const bool zz = (z < 2 * EPS) && cw2[kk] != 0u;
-            const bool in = ((dr[kk] & dc[kk]) < 0) && !zz;   // below both certain-in limits
-            rz[kk] = (((unsigned)dr[kk] < (unsigned)rp.z) && cw2[kk] != 0u) || zz;
-            cz[kk] = (unsigned)dc[kk] < cw2[kk];
-            nib |= in ? (1u << kk) : 0u;
-            anyc |= rz[kk] | cz[kk];
+            dr[kk] = rb + ynv[kk] - sw.T[kk];
+            dc[kk] = rp.x + ycl[kk] - sw.T[kk];
+            // cells with a (near-)zero squared distance always take the exact evaluation, so a negative
+            // exact item (NaN distance, F7) is detected exactly like in the reference order
+            const bool zz = z < 2 * EPS;
+            const bool in = ((dr[kk] & dc[kk]) < 0) && !zz;   // certainly below both thresholds
+            v |= in ? (kk ? bit1 : bit0) : 0u;
+            anyc |= zz | ((unsigned)dr[kk] < (unsigned)rp.z) | ((unsigned)dc[kk] < cw2[kk]);
         }
-        // the lane's RC bits sit at strip bit RC*lane - HALO; assemble the 64-bit strip pattern
-        const int pos = RC * lane - HALO;                     // may be negative for halo lanes (nib == 0 there)
-        unsigned long long pat = (pos >= 0) ? ((unsigned long long)nib << pos) : 0ull;
-        unsigned p0 = __reduce_or_sync(0xffffffffu, (unsigned)pat);
-        unsigned p1 = __reduce_or_sync(0xffffffffu, (unsigned)(pat >> 32));
-        if (lane == 0) {
-            const unsigned long long P = ((unsigned long long)p1 << 32) | p0;   // bits 0..55
-            uint32_t *rowp = crp + (int64_t)i * words + wlo;
-            const unsigned w0 = (unsigned)(P << bsh);
-            const unsigned w1 = (unsigned)((bsh ? (P >> (32 - bsh)) : (P >> 32)));
-            const unsigned w2 = bsh ? (unsigned)(P >> (64 - bsh)) : 0u;
-            if (w0) atomicOr(rowp, w0);
-            if (w1) atomicOr(rowp + 1, w1);
-            if (w2) atomicOr(rowp + 2, w2);
-        }
-        if (__any_sync(0xffffffffu, anyc)) {
+        const unsigned w0 = __reduce_or_sync(full, v & sel0);
+        const unsigned w1 = __reduce_or_sync(full, v & sel1);
+        const unsigned w2 = __reduce_or_sync(full, v & sel2);
+        const unsigned wv = lane == 0 ? w0 : (lane == 1 ? w1 : w2);
+        if (lane < 3 && wv) atomicOr(rowp, wv);
+        rowp += words;
+        if (__any_sync(full, anyc)) {
+            // uncertain cells go to this strip's private list (no returning atomics in the sweep):
+            // entry = i | j << 14 | row-zone << 28 | below-row-bracket << 29 | col-zone << 30 | below-col-bracket << 31
+            const int i = a - HALO;                           // query window (CRP row); i < Mx by construction
 #pragma unroll
             for (int kk = 0; kk < RC; ++kk) {
-                if (rz[kk]) {
-                    const unsigned p = atomicAdd(&cnt[i], 1u);
-                    if (p < CAND_CAP) cand[(size_t)i * CAND_CAP + p] = (uint16_t)(jcol[kk] | (dr[kk] < 2 * EPS ? 0x8000 : 0));
-                    // (zero-zone cells far below the bracket have dr < 0 < 2 EPS: counted as "below", consistent with cb)
+                const bool zz = (rp.x + ynv[kk] - sw.T[kk]) < 2 * EPS;
+                const bool rz = (((unsigned)dr[kk] < (unsigned)rp.z) && cw2[kk] != 0u) || zz;
+                const bool cz = (unsigned)dc[kk] < cw2[kk];
+                const unsigned m = __ballot_sync(full, rz | cz);
+                if (rz | cz) {
+                    const unsigned pos = nlist + __popc(m & ltmask);
+                    if (pos < SLIST_CAP)
+                        slist[pos] = (unsigned)i | ((unsigned)jcol[kk] << 14) | (rz ? 1u << 28 : 0u) |
+                                     ((rz && dr[kk] < 2 * EPS) ? 1u << 29 : 0u) | (cz ? 1u << 30 : 0u) |
+                                     ((cz && dc[kk] < 2 * EPS) ? 1u << 31 : 0u);
                 }
-                if (cz[kk]) {
-                    const int line = L.max_rows + jcol[kk];
-                    const unsigned p = atomicAdd(&cnt[line], 1u);
-                    if (p < CAND_CAP) cand[(size_t)line * CAND_CAP + p] = (uint16_t)(i | (dc[kk] < 2 * EPS ? 0x8000 : 0));
-                }
+                nlist += __popc(m);
             }
         }
     });
     (void)Mx;
+    if (lane == 0) slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[strip] = nlist;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter: strip lists -> per-row / per-column candidate lists (the returning atomics live here, in a
+// kernel with enough parallelism to hide them)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) fast_scatter_kernel(int n, FastLayout L, char *__restrict__ scratch,
+                                                           int64_t first, uint32_t *__restrict__ status) {
+    const int slot = blockIdx.y, strip = blockIdx.x;
+    if (slot >= n) return;
+    const uint32_t cntv = slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[strip];
+    if (cntv > SLIST_CAP && threadIdx.x == 0) atomicOr(&status[first + slot], PAIR_ST_FALLBACK);
+    const uint32_t m = min(cntv, (uint32_t)SLIST_CAP);
+    const uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * SLIST_CAP;
+    uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
+    uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
+    for (uint32_t e = threadIdx.x; e < m; e += blockDim.x) {
+        const uint32_t v = slist[e];
+        const int i = v & 0x3fff, j = (v >> 14) & 0x3fff;
+        if (v & (1u << 28)) {
+            const unsigned p = atomicAdd(&cnt[i], 1u);
+            if (p < CAND_CAP) cand[(size_t)i * CAND_CAP + p] = (uint16_t)(j | ((v >> 29) & 1u) << 15);
+        }
+        if (v & (1u << 30)) {
+            const int line = L.max_rows + j;
+            const unsigned p = atomicAdd(&cnt[line], 1u);
+            if (p < CAND_CAP) cand[(size_t)line * CAND_CAP + p] = (uint16_t)(i | ((v >> 31) & 1u) << 15);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -670,6 +706,8 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     CUDA_TRY(cudaGetLastError());
     fast_emit_kernel<RC><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
     CUDA_TRY(cudaGetLastError());
+    fast_scatter_kernel<<<dim3(strips_c, n), 128, 0, st>>>(n, L, base, first, status);
+    CUDA_TRY(cudaGetLastError());
     const int lines = g.max_rows + g.max_cols;
     fast_resolve_thr_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(ts, pairs, first, n, L, base, p.integer_guard, unit,
                                                                        thr_q, thr_r, status);
@@ -677,7 +715,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     fast_resolve_bits_kernel<<<dim3((lines * CAND_CAP + 255) / 256, n), 256, 0, st>>>(n, L, base, thr_q, thr_r, crp, g.words,
                                                                                       g.crp_words);
     CUDA_TRY(cudaGetLastError());
-    if (launches) *launches += 9;
+    if (launches) *launches += 10;
     return ACOSS_OK;
 }
 
