@@ -246,8 +246,10 @@ def main():
     # ---- end to end through the plugin API (host buffers in, host score matrix out) -----------
     feats = [dict(hpcp=t_, label=str(l)) for t_, l in zip(tracks, labels)]
     cache = os.path.join("/tmp", "acoss_bench_cache_%d" % rank)
-    alg = Serra09(None, None, features=feats, downsample_fac=1, shortname="bench%d" % rank, device=local,
-                  cachedir=cache, engine=eng)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):               # keep stdout to the one JSON line
+        alg = Serra09(None, None, features=feats, downsample_fac=1, shortname="bench%d" % rank, device=local,
+                      cachedir=cache, engine=eng)
     alg._resident = True                                       # tracks already resident in this engine
     alg.crp_path = params.crp_path
     host_pairs = [mine[k * P:(k + 1) * P].astype(np.int64) for k in range(total_steps)]

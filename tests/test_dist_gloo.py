@@ -1,0 +1,74 @@
+"""World-size-2 (and 3) gloo tests of the multi-GPU host logic: cell-balanced sharding of the pair
+list, variable-length all_gather of score slices, scatter into the score matrix."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_score(pairs):
+    p = np.asarray(pairs, dtype=np.int64)
+    return ((p[:, 0] * 131 + p[:, 1] * 7) % 1000).astype(np.float32) / 8.0
+
+
+def _worker(rank, world, port, tmp, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    os.chdir(tmp)
+    import torch.distributed as dist
+    from acoss_b200.distributed import all_pairwise_distributed
+    from acoss_b200.serra09 import Serra09
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    feats = [dict(hpcp=rng.random((int(n), 12)).astype(np.float32), label=str(i // 3))
+             for i, n in enumerate(rng.integers(20, 200, size=17))]
+    alg = Serra09(None, None, features=feats, downsample_fac=1, shortname="r%d" % rank, cachedir="cache%d" % rank)
+    bounds = all_pairwise_distributed(alg, symmetric=True, score_fn=_fake_score)
+    q.put((rank, np.array(alg.Ds["main"]), bounds))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_all_pairwise_gloo(tmp_path, world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 17
+    i, j = np.triu_indices(n, k=1)
+    want = np.zeros((n, n), np.float32)
+    want[i, j] = _fake_score(np.stack([i, j], 1))
+    want = want + want.T
+    for rank, D, bounds in res:
+        assert np.array_equal(D, want)                      # byte-identical gathered matrix on every rank
+        assert bounds[0] == 0 and bounds[-1] == n * (n - 1) // 2 and (np.diff(bounds) > 0).all()
+
+
+def test_shard_bounds_balance():
+    from acoss_b200.distributed import shard_bounds
+    rng = np.random.default_rng(0)
+    w = rng.integers(1, 100, size=1000).astype(np.float64)
+    for world in (1, 2, 4, 8):
+        b = shard_bounds(w, world)
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == 1000 and (np.diff(b) >= 0).all()
+        loads = [w[b[r]:b[r + 1]].sum() for r in range(world)]
+        assert max(loads) - min(loads) <= 2 * w.max()
+    assert list(shard_bounds([], 4)) == [0, 0, 0, 0, 0]
+    assert list(shard_bounds([5.0], 2)) in ([0, 0, 1], [0, 1, 1])
