@@ -198,11 +198,9 @@ struct Sweep {
         }
     }
 
-    // one streamed frame (12 floats in three float4): updates T for the lane's RC columns.
-    // U = a % 9 (static ring slot).
-    template <int U>
-    __device__ __forceinline__ void row(const float4 &x0, const float4 &x1, const float4 &x2) {
-        int eb[RC], old[RC];
+    // frame-level dot products of one streamed frame (12 floats in three float4) with the lane's RC owned
+    // frames, quantised to fixed point (raw float bits of e + magic)
+    __device__ __forceinline__ void dot(const float4 &x0, const float4 &x1, const float4 &x2, int (&eb)[RC]) const {
 #pragma unroll
         for (int k = 0; k < RC; ++k) {
             float acc = __fmul_rn(x0.x, y[k][0]);
@@ -212,6 +210,12 @@ struct Sweep {
             acc = __fmaf_rn(x2.z, y[k][10], acc); acc = __fmaf_rn(x2.w, y[k][11], acc);
             eb[k] = __float_as_int(__fadd_rn(acc, magic));
         }
+    }
+
+    // slides the diagonal sums T by one row.  U = a % 9 (static ring slot).
+    template <int U>
+    __device__ __forceinline__ void finish(const int (&eb)[RC]) {
+        int old[RC];
         // e[a-9][c-9]: column c-9 lives dl lanes to the left, in register (k - 9) mod RC of ring slot U
 #pragma unroll
         for (int k = 0; k < RC; ++k) {
@@ -232,8 +236,9 @@ struct Sweep {
 template <int V> struct IC { static constexpr int value = V; };
 template <bool V> struct BC { static constexpr bool value = V; };
 
-// Drives a sweep over streamed frames 0 .. nrows-1 (nrows >= 10 always: Mx >= 2).  The next frame and
-// the next row's parameter word are prefetched into registers one row ahead.  fn(a, param) runs for
+// Drives a sweep over streamed frames 0 .. nrows-1 (nrows >= 10 always: Mx >= 2).  The next frame is
+// loaded into the frame registers as soon as the dot products have consumed them, the next row's
+// parameter word right after its use: loads overlap the rest of the row, no register copies.  fn(a, param) runs for
 // rows a >= HALO, param = P[a - HALO].
 template <int RC, typename PT, typename Fn>
 __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict__ X, const PT *__restrict__ P,
@@ -246,15 +251,15 @@ __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict
     auto step = [&](auto uc, auto callc, auto pfc) {
         constexpr int U = decltype(uc)::value;
         constexpr bool CALL = decltype(callc)::value, PF = decltype(pfc)::value;
+        int eb[RC];
+        sw.dot(c0, c1, c2, eb);
+        // the frame registers are dead now: refill them with the next row while this row finishes
         px += 3;
-        const float4 n0 = __ldg(px), n1 = __ldg(px + 1), n2 = __ldg(px + 2);
-        PT pn{};
-        if (PF) pn = __ldg(pp + a + 1);
-        sw.template row<U>(c0, c1, c2);
+        c0 = __ldg(px); c1 = __ldg(px + 1); c2 = __ldg(px + 2);
+        sw.template finish<U>(eb);
         if (CALL) fn(a, pc);
+        if (PF) pc = __ldg(pp + a + 1);
         ++a;
-        c0 = n0; c1 = n1; c2 = n2;
-        if (PF) pc = pn;
     };
     // rows 0..8: the diagonal sums fill up; only row 8 produces a window
     step(IC<0>{}, BC<false>{}, BC<false>{}); step(IC<1>{}, BC<false>{}, BC<false>{}); step(IC<2>{}, BC<false>{}, BC<false>{});
