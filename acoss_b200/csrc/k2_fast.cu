@@ -33,7 +33,8 @@ constexpr int NBIN = 64;            // histogram bins per level (+1 overflow row
 constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
 constexpr int CAND_CAP = 32;        // candidates per row / column
 constexpr int WPC = 4;              // warps per CTA in the sweep kernels
-constexpr int SLIST_CAP = 2048;     // uncertain cells one emit strip may record before the pair is flagged
+constexpr int RCV = 4;              // owned frames per lane (register columns) in the sweep kernels
+constexpr int SLIST_CAP = 4096;     // uncertain cells one emit strip may record before the pair is flagged
 
 struct PairHdr {                    // per-slot header written by fast_prep_kernel
     int32_t nq, nr, Mx, Nx;         // frames and stacked windows of query / reference
@@ -73,7 +74,7 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.off_cand = take((size_t)L.lines * CAND_CAP * 2);
     L.off_candd = take((size_t)L.lines * CAND_CAP * 4);
     L.off_rowpack = take((size_t)g.max_rows * 16);
-    L.strips_c = (g.max_cols + (32 * 2 - HALO) - 1) / (32 * 2 - HALO);
+    L.strips_c = (g.max_cols + (32 * RCV - HALO) - 1) / (32 * RCV - HALO);
     L.off_slist = take((size_t)L.strips_c * SLIST_CAP * 4);
     L.off_scnt = take((size_t)L.strips_c * 4);
     L.slot_bytes = align_up(o, 256);
@@ -289,13 +290,14 @@ __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict
 // LEVEL = 2: fine bins -> final bracket [lo, lo + w) holding ranks floor(k) and ceil(k).
 // ------------------------------------------------------------------------------------------------
 template <int RC, int ORIENT, int LEVEL>
-__global__ void __launch_bounds__(32 * WPC, 5) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+__global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
                                                              uint32_t *__restrict__ status) {
-    extern __shared__ uint32_t s_hist[];                      // [WPC][NBIN + 1][32], two 16-bit counters per word
+    extern __shared__ uint32_t s_hist[];                      // [WPC][NBIN + 1][RC / 2][32], two 16-bit counters per word
     using SW = Sweep<RC>;
-    static_assert(RC == 2, "histogram packing is written for RC == 2");
+    static_assert(RC % 2 == 0, "histogram packing needs an even number of register columns");
+    constexpr int HW = RC / 2;                                // words per (bin, lane)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t task = (int64_t)blockIdx.x * WPC + warp;
     const int slot = (int)(task / strips_max), strip = (int)(task % strips_max);
@@ -330,9 +332,9 @@ __global__ void __launch_bounds__(32 * WPC, 5) fast_hist_kernel(TrackSet ts, con
         ynrel[kk] = valid[kk] ? yn[j] - lo_a[j] : 0x40000000;  // invalid columns land in the overflow bin
         shf[kk] = valid[kk] ? sh_a[j] : 0;
     }
-    uint32_t *hist = s_hist + (size_t)warp * (NBIN + 1) * 32 + lane;
+    uint32_t *hist = s_hist + (size_t)warp * (NBIN + 1) * HW * 32 + lane;
 #pragma unroll 1
-    for (int b = 0; b <= NBIN; ++b) hist[b * 32] = 0u;
+    for (int b = 0; b < (NBIN + 1) * HW; ++b) hist[b * 32] = 0u;
     __syncwarp();
 
     const int nrows = nX - 1;                                 // streamed frames 0 .. nX-2 (F4: last frame unused)
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(32 * WPC, 5) fast_hist_kernel(TrackSet ts, con
         for (int kk = 0; kk < RC; ++kk) {
             const unsigned zr = (unsigned)(xb + ynrel[kk] - sw.T[kk]);
             const unsigned idx = min(zr >> shf[kk], (unsigned)NBIN);
-            atomicAdd(&hist[idx * 32], 1u << (16 * kk));   // thread-private bank: conflict-free shared atomic
+            atomicAdd(&hist[(idx * HW + kk / 2) * 32], 1u << (16 * (kk & 1)));   // thread-private bank: conflict-free
         }
     });
     __syncwarp();
@@ -351,12 +353,12 @@ __global__ void __launch_bounds__(32 * WPC, 5) fast_hist_kernel(TrackSet ts, con
     for (int kk = 0; kk < RC; ++kk) {
         if (!valid[kk]) continue;
         const int j = cb + RC * lane + kk - HALO;
-        const uint32_t *hp = hist;
-        const int hs = 16 * kk;
+        const uint32_t *hp = hist + (kk / 2) * 32;
+        const int hs = 16 * (kk & 1);
         const int base = cb_a[j];                             // items below lo (from the previous level)
         int cum = base, b1 = -1, b2 = -1, cb1 = 0, cend = 0;
         for (int b = 0; b < NBIN; ++b) {
-            const int c = (hp[b * 32] >> hs) & 0xffff;
+            const int c = (hp[b * HW * 32] >> hs) & 0xffff;
             if (b1 < 0 && cum + c > fk) { b1 = b; cb1 = cum; }
             if (b2 < 0 && cum + c > ck) { b2 = b; cend = cum + c; }
             cum += c;
@@ -390,13 +392,14 @@ __global__ void __launch_bounds__(32 * WPC, 5) fast_hist_kernel(TrackSet ts, con
 // emit sweep (orientation 0: owned = reference columns, streamed = query rows)
 // ------------------------------------------------------------------------------------------------
 template <int RC>
-__global__ void __launch_bounds__(32 * WPC, 4) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+__global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
                                                              uint32_t *__restrict__ crp_all, int words,
                                                              int64_t crp_words) {
     using SW = Sweep<RC>;
-    static_assert(RC == 2, "emit word assembly is written for RC == 2");
+    static_assert(RC == 2 || RC == 4, "emit word assembly needs RC bits per lane that never straddle a word");
+    constexpr int NW = (24 + 32 * RC + 31) / 32;              // CRP words one strip row can touch
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t task = (int64_t)blockIdx.x * WPC + warp;
     const int slot = (int)(task / strips_max), strip = (int)(task % strips_max);
@@ -433,14 +436,16 @@ __global__ void __launch_bounds__(32 * WPC, 4) fast_emit_kernel(TrackSet ts, con
         cw2[kk] = valid ? (unsigned)(w_c[j] + 4 * EPS) : 0u;
     }
     // output placement: strip bit t = RC*lane + kk - HALO <-> CRP column cb + t.  cb is a multiple of 8 and the
-    // lane's RC = 2 bits start at an even position, so they never straddle a 32-bit word: every lane
-    // contributes its bits to word lword of the row at a position that is constant over the sweep.
+    // lane's RC bits start at a multiple of RC, so they never straddle a 32-bit word: every lane contributes
+    // its bits to word lword of the row at a position that is constant over the sweep.
     const int gpos = (cb & 31) + RC * lane - HALO;
     const int lword = gpos >> 5;                              // -1 for halo lanes (they contribute nothing)
-    const unsigned bit0 = (lword >= 0) ? (1u << (gpos & 31)) : 0u, bit1 = bit0 << 1;
-    const unsigned sel0 = lword == 0 ? 0xffffffffu : 0u, sel1 = lword == 1 ? 0xffffffffu : 0u, sel2 = lword == 2 ? 0xffffffffu : 0u;
+    const int lbit = gpos & 31;
+    unsigned bitk[RC];
+#pragma unroll
+    for (int kk = 0; kk < RC; ++kk) bitk[kk] = (lword >= 0) ? (1u << (lbit + kk)) : 0u;
     const unsigned full = __activemask();                     // all 32 lanes (kept in a register)
-    uint32_t *rowp = crp + (cb >> 5) + ((lane < 3) ? lane : 0);   // advances by `words` per row
+    uint32_t *rowp = crp + (cb >> 5) + ((lane < NW) ? lane : 0);   // advances by `words` per row
     const int nrows = nX - 1;
     run_sweep<RC, int4>(sw, X, rowpack, nrows, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
         const int rb = rp.x - rp.y;                           // dr = z - (rowLo - 2 EPS) = rb + bb - T
@@ -456,14 +461,16 @@ __global__ void __launch_bounds__(32 * WPC, 4) fast_emit_kernel(TrackSet ts, con
             // exact item (NaN distance, F7) is detected exactly like in the reference order
             const bool zz = z < 2 * EPS;
             const bool in = ((dr[kk] & dc[kk]) < 0) && !zz;   // certainly below both thresholds
-            v |= in ? (kk ? bit1 : bit0) : 0u;
+            v |= in ? bitk[kk] : 0u;
             anyc |= zz | ((unsigned)dr[kk] < (unsigned)rp.z) | ((unsigned)dc[kk] < cw2[kk]);
         }
-        const unsigned w0 = __reduce_or_sync(full, v & sel0);
-        const unsigned w1 = __reduce_or_sync(full, v & sel1);
-        const unsigned w2 = __reduce_or_sync(full, v & sel2);
-        const unsigned wv = lane == 0 ? w0 : (lane == 1 ? w1 : w2);
-        if (lane < 3 && wv) atomicOr(rowp, wv);
+        unsigned wv = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const unsigned ww = __reduce_or_sync(full, lword == w ? v : 0u);
+            wv = (lane == w) ? ww : wv;
+        }
+        if (lane < NW && wv) atomicOr(rowp, wv);
         rowp += words;
         if (__any_sync(full, anyc)) {
             // uncertain cells go to this strip's private list (no returning atomics in the sweep):
@@ -680,7 +687,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
                    const acoss_params &p, const SlotGeom &g, void *scratch, size_t slot_bytes, uint32_t *crp,
                    float *thr_q, float *thr_r, uint32_t *status, cudaStream_t st, int64_t *launches) {
     if (n <= 0) return ACOSS_OK;
-    constexpr int RC = 2;
+    constexpr int RC = RCV;
     const FastLayout L = make_layout(g, ts.max_frames);
     if (L.slot_bytes != slot_bytes) { acoss_set_error("fast path: scratch layout mismatch"); return ACOSS_E_INVALID; }
     char *base = (char *)scratch;
@@ -694,7 +701,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     CUDA_TRY(cudaGetLastError());
     const int outw = Sweep<RC>::OUTW;
     const int strips_c = (g.max_cols + outw - 1) / outw, strips_r = (g.max_rows + outw - 1) / outw;
-    const size_t smem = (size_t)WPC * (NBIN + 1) * 32 * 4;
+    const size_t smem = (size_t)WPC * (NBIN + 1) * (RC / 2) * 32 * 4;
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
