@@ -388,6 +388,24 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
     }
 }
 
+// Rare path of the emit sweep, kept out of line so the sweep loop stays small: lanes with c set append
+// one entry each to the strip-private list (warp-aggregated positions, no atomics).
+//   entry = i | j << 14 | row-zone << 28 | below-row-bracket << 29 | col-zone << 30 | below-col-bracket << 31
+__device__ __noinline__ unsigned emit_append(uint32_t *__restrict__ slist, unsigned nlist, bool c, int ar, int ac, int zp,
+                                             int rw1, int cw1, int i, int j) {
+    const unsigned m = __ballot_sync(0xffffffffu, c);
+    if (c) {
+        const bool zz = zp < 0;                                 // z < 2 EPS
+        const bool rz = ((ar | (rw1 - ar)) >= 0) || zz;
+        const bool cz = (ac | (cw1 - ac)) >= 0;
+        const unsigned pos = nlist + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+        if (pos < SLIST_CAP)
+            slist[pos] = (unsigned)i | ((unsigned)j << 14) | (rz ? 1u << 28 : 0u) | ((rz && ar < 2 * EPS) ? 1u << 29 : 0u) |
+                         (cz ? 1u << 30 : 0u) | ((cz && ac < 2 * EPS) ? 1u << 31 : 0u);
+    }
+    return nlist + __popc(m);
+}
+
 // ------------------------------------------------------------------------------------------------
 // emit sweep (orientation 0: owned = reference columns, streamed = query rows)
 // ------------------------------------------------------------------------------------------------
@@ -418,22 +436,20 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
     const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
     uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * SLIST_CAP;
     unsigned nlist = 0u;
-    const unsigned ltmask = (1u << lane) - 1u;
     uint32_t *crp = crp_all + (int64_t)slot * crp_words;
 
     SW sw;
     sw.init(Y, nY, cb, lane, magic);
-    int ynv[RC], ycl[RC];                                     // bb_fix[j] and bb_fix[j] - (colLo - 2 EPS)
-    unsigned cw2[RC];                                         // colW + 4 EPS (0 for columns this lane does not emit)
+    int ynv[RC], ycl[RC], cw1[RC];                            // bb_fix[j], bb_fix[j] - (colLo - 2 EPS), colW + 4 EPS - 1
     int jcol[RC];
 #pragma unroll
     for (int kk = 0; kk < RC; ++kk) {
         const int j = cb + RC * lane + kk - HALO;
         const bool valid = (j >= cb) && (j < My) && (j < cb + SW::OUTW);
         jcol[kk] = j;
-        ynv[kk] = valid ? yn[j] : 0x20000000;                 // invalid: z huge => never in, never near zero
+        ynv[kk] = valid ? yn[j] : 0x20000000;                 // invalid: z huge => never in, never a candidate
         ycl[kk] = valid ? yn[j] - (lo_c[j] - 2 * EPS) : 0x20000000;
-        cw2[kk] = valid ? (unsigned)(w_c[j] + 4 * EPS) : 0u;
+        cw1[kk] = valid ? w_c[j] + 4 * EPS - 1 : -1;
     }
     // output placement: strip bit t = RC*lane + kk - HALO <-> CRP column cb + t.  cb is a multiple of 8 and the
     // lane's RC bits start at a multiple of RC, so they never straddle a 32-bit word: every lane contributes
@@ -447,22 +463,25 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
     const unsigned full = __activemask();                     // all 32 lanes (kept in a register)
     uint32_t *rowp = crp + (cb >> 5) + ((lane < NW) ? lane : 0);   // advances by `words` per row
     const int nrows = nX - 1;
+    // Per cell, with z the fixed-point item (sign-bit arithmetic, no predicates):
+    //   ar = z - (rowLo - 2 EPS), ac = z - (colLo - 2 EPS), zp = z - 2 EPS
+    //   certainly in  <=> ar < 0 and ac < 0 and zp >= 0                      sign(ar & ac & ~zp)
+    //   row zone      <=> 0 <= ar <= rw1 (rw1 = rowW + 4 EPS - 1)            !sign(ar | (rw1 - ar))
+    //   uncertain     <=> row zone or column zone or zp < 0 (near-zero item, so F7's NaN is caught exactly)
     run_sweep<RC, int4>(sw, X, rowpack, nrows, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
-        const int rb = rp.x - rp.y;                           // dr = z - (rowLo - 2 EPS) = rb + bb - T
-        int dr[RC], dc[RC];
+        const int xr = rp.x - rp.y, xp = rp.x - 2 * EPS, rw1 = rp.z - 1;
+        int ar[RC], ac[RC], zp[RC], ns[RC];
         unsigned v = 0u;
-        bool anyc = false;
+        int nsall = -1;
 #pragma unroll
         for (int kk = 0; kk < RC; ++kk) {
-            const int z = rp.x + ynv[kk] - sw.T[kk];
-            dr[kk] = rb + ynv[kk] - sw.T[kk];
-            dc[kk] = rp.x + ycl[kk] - sw.T[kk];
-            // cells with a (near-)zero squared distance always take the exact evaluation, so a negative
-            // exact item (NaN distance, F7) is detected exactly like in the reference order
-            const bool zz = z < 2 * EPS;
-            const bool in = ((dr[kk] & dc[kk]) < 0) && !zz;   // certainly below both thresholds
-            v |= in ? bitk[kk] : 0u;
-            anyc |= zz | ((unsigned)dr[kk] < (unsigned)rp.z) | ((unsigned)dc[kk] < cw2[kk]);
+            ar[kk] = xr + ynv[kk] - sw.T[kk];
+            ac[kk] = rp.x + ycl[kk] - sw.T[kk];
+            zp[kk] = xp + ynv[kk] - sw.T[kk];
+            const int zr = ar[kk] | (rw1 - ar[kk]), zc = ac[kk] | (cw1[kk] - ac[kk]);
+            ns[kk] = zr & zc & ~zp[kk];                        // sign set <=> NOT uncertain
+            nsall &= ns[kk];
+            v |= (unsigned)((ar[kk] & ac[kk] & ~zp[kk]) >> 31) & bitk[kk];
         }
         unsigned wv = 0u;
 #pragma unroll
@@ -472,25 +491,12 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
         }
         if (lane < NW && wv) atomicOr(rowp, wv);
         rowp += words;
-        if (__any_sync(full, anyc)) {
-            // uncertain cells go to this strip's private list (no returning atomics in the sweep):
-            // entry = i | j << 14 | row-zone << 28 | below-row-bracket << 29 | col-zone << 30 | below-col-bracket << 31
+        if (__any_sync(full, nsall >= 0)) {
             const int i = a - HALO;                           // query window (CRP row); i < Mx by construction
 #pragma unroll
-            for (int kk = 0; kk < RC; ++kk) {
-                const bool zz = (rp.x + ynv[kk] - sw.T[kk]) < 2 * EPS;
-                const bool rz = (((unsigned)dr[kk] < (unsigned)rp.z) && cw2[kk] != 0u) || zz;
-                const bool cz = (unsigned)dc[kk] < cw2[kk];
-                const unsigned m = __ballot_sync(full, rz | cz);
-                if (rz | cz) {
-                    const unsigned pos = nlist + __popc(m & ltmask);
-                    if (pos < SLIST_CAP)
-                        slist[pos] = (unsigned)i | ((unsigned)jcol[kk] << 14) | (rz ? 1u << 28 : 0u) |
-                                     ((rz && dr[kk] < 2 * EPS) ? 1u << 29 : 0u) | (cz ? 1u << 30 : 0u) |
-                                     ((cz && dc[kk] < 2 * EPS) ? 1u << 31 : 0u);
-                }
-                nlist += __popc(m);
-            }
+            for (int kk = 0; kk < RC; ++kk)
+                if (__any_sync(full, ns[kk] >= 0))
+                    nlist = emit_append(slist, nlist, ns[kk] >= 0, ar[kk], ac[kk], zp[kk], rw1, cw1[kk], i, jcol[kk]);
         }
     });
     (void)Mx;
