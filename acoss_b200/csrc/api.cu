@@ -46,6 +46,7 @@ struct acoss_ctx {
     uint32_t *h_flag = nullptr;   // pinned
     int64_t stats[8] = {0};
     int pending_status_check = 0;
+    int stats_reason_pending = 0;
     int64_t pending_pairs = 0;
     // optional per-stage timing (CUDA events on the context stream)
     int profiling = 0;
@@ -382,6 +383,7 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     c->pending_pairs = K;
     c->stats[0] = K;
     c->stats[2] = launches;
+    c->stats_reason_pending = 1;
     return ACOSS_OK;
 }
 
@@ -392,6 +394,7 @@ int acoss_sync(acoss_ctx *c) {
     fold_spans(c);
     if (c->pending_status_check) {
         c->pending_status_check = 0;
+        c->stats[5] = c->h_flag[0];
         if (c->h_flag[0] & PAIR_ST_NAN) {
             acoss_set_error("a squared distance was negative -> NaN distance (essentia would raise: non-binary CRP, F7)");
             return ACOSS_E_NAN;

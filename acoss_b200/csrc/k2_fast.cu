@@ -31,10 +31,9 @@ constexpr int M9 = 9;               // frameStackSize handled by this path
 constexpr int HALO = M9 - 1;        // owned columns a strip recomputes (8)
 constexpr int NBIN = 64;            // histogram bins per level (+1 overflow row)
 constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
-constexpr int CAND_CAP = 32;        // candidates per row / column
+constexpr int CAND_CAP = 64;        // candidates per row / column
 constexpr int WPC = 4;              // warps per CTA in the sweep kernels
 constexpr int RCV = 4;              // owned frames per lane (register columns) in the sweep kernels
-constexpr int SLIST_CAP = 4096;     // uncertain cells one emit strip may record before the pair is flagged
 
 struct PairHdr {                    // per-slot header written by fast_prep_kernel
     int32_t nq, nr, Mx, Nx;         // frames and stacked windows of query / reference
@@ -49,7 +48,7 @@ struct FastLayout {
     size_t slot_bytes;
     size_t off_hdr, off_rrot, off_aaf, off_bbf, off_aai, off_bbi, off_lo, off_w, off_cb, off_sh, off_cnt,
         off_cand, off_candd, off_rowpack, off_slist, off_scnt;
-    int max_rows, max_cols, max_frames, lines, strips_c;
+    int max_rows, max_cols, max_frames, lines, strips_c, slist_cap;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -75,7 +74,9 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.off_candd = take((size_t)L.lines * CAND_CAP * 4);
     L.off_rowpack = take((size_t)g.max_rows * 16);
     L.strips_c = (g.max_cols + (32 * RCV - HALO) - 1) / (32 * RCV - HALO);
-    L.off_slist = take((size_t)L.strips_c * SLIST_CAP * 4);
+    L.slist_cap = 4096;                                   // uncertain cells one emit strip may record
+    while (L.slist_cap < 3 * g.max_rows) L.slist_cap *= 2;
+    L.off_slist = take((size_t)L.strips_c * L.slist_cap * 4);
     L.off_scnt = take((size_t)L.strips_c * 4);
     L.slot_bytes = align_up(o, 256);
     return L;
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
         }
         const int sh = shf[kk], lo = lo_a[j];
         if (b1 < 0 || b2 < 0) {                               // ranks not inside the binned range
-            atomicOr(&status[k], PAIR_ST_FALLBACK);
+            atomicOr(&status[k], PAIR_ST_FALLBACK | 4u);      // reason 4: rank outside the binned range
             continue;
         }
         if (LEVEL == 1) {
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
             lo_a[j] = lo + (b1 << sh);
             w_a[j] = (b2 - b1 + 1) << sh;
             cb_a[j] = cb1;
-            if (cend - cb1 > CAND_CAP - 8) atomicOr(&status[k], PAIR_ST_FALLBACK);   // bracket too crowded (ties)
+            if (cend - cb1 > CAND_CAP - 8) atomicOr(&status[k], PAIR_ST_FALLBACK | 8u);   // reason 8: bracket too crowded (ties)
             if (ORIENT == 1) {
                 int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
                 rowpack[j] = make_int4(yn[j], lo + (b1 << sh) - 2 * EPS, ((b2 - b1 + 1) << sh) + 4 * EPS, 0);
@@ -391,15 +392,15 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
 // Rare path of the emit sweep, kept out of line so the sweep loop stays small: lanes with c set append
 // one entry each to the strip-private list (warp-aggregated positions, no atomics).
 //   entry = i | j << 14 | row-zone << 28 | below-row-bracket << 29 | col-zone << 30 | below-col-bracket << 31
-__device__ __noinline__ unsigned emit_append(uint32_t *__restrict__ slist, unsigned nlist, bool c, int ar, int ac, int zp,
-                                             int rw1, int cw1, int i, int j) {
+__device__ __noinline__ unsigned emit_append(uint32_t *__restrict__ slist, unsigned nlist, unsigned cap, bool c, int ar, int ac,
+                                             int zp, int rw1, int cw1, int i, int j) {
     const unsigned m = __ballot_sync(0xffffffffu, c);
     if (c) {
         const bool zz = zp < 0;                                 // z < 2 EPS
         const bool rz = ((ar | (rw1 - ar)) >= 0) || zz;
         const bool cz = (ac | (cw1 - ac)) >= 0;
         const unsigned pos = nlist + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
-        if (pos < SLIST_CAP)
+        if (pos < cap)
             slist[pos] = (unsigned)i | ((unsigned)j << 14) | (rz ? 1u << 28 : 0u) | ((rz && ar < 2 * EPS) ? 1u << 29 : 0u) |
                          (cz ? 1u << 30 : 0u) | ((cz && ac < 2 * EPS) ? 1u << 31 : 0u);
     }
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
     const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
     const int32_t *lo_c = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + L.max_rows;
     const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
-    uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * SLIST_CAP;
+    uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * L.slist_cap;
     unsigned nlist = 0u;
     uint32_t *crp = crp_all + (int64_t)slot * crp_words;
 
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
 #pragma unroll
             for (int kk = 0; kk < RC; ++kk)
                 if (__any_sync(full, ns[kk] >= 0))
-                    nlist = emit_append(slist, nlist, ns[kk] >= 0, ar[kk], ac[kk], zp[kk], rw1, cw1[kk], i, jcol[kk]);
+                    nlist = emit_append(slist, nlist, (unsigned)L.slist_cap, ns[kk] >= 0, ar[kk], ac[kk], zp[kk], rw1, cw1[kk], i, jcol[kk]);
         }
     });
     (void)Mx;
@@ -512,9 +513,9 @@ __global__ void __launch_bounds__(128) fast_scatter_kernel(int n, FastLayout L, 
     const int slot = blockIdx.y, strip = blockIdx.x;
     if (slot >= n) return;
     const uint32_t cntv = slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[strip];
-    if (cntv > SLIST_CAP && threadIdx.x == 0) atomicOr(&status[first + slot], PAIR_ST_FALLBACK);
-    const uint32_t m = min(cntv, (uint32_t)SLIST_CAP);
-    const uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * SLIST_CAP;
+    if (cntv > (uint32_t)L.slist_cap && threadIdx.x == 0) atomicOr(&status[first + slot], PAIR_ST_FALLBACK | 16u);   // reason 16: strip list overflow
+    const uint32_t m = min(cntv, (uint32_t)L.slist_cap);
+    const uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * L.slist_cap;
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
     for (uint32_t e = threadIdx.x; e < m; e += blockDim.x) {
@@ -603,10 +604,10 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
     const int32_t w = slot_ptr<int32_t>(scratch, L, slot, L.off_w)[line];
     const int c0 = slot_ptr<int32_t>(scratch, L, slot, L.off_cb)[line] - nbelow;   // items below every candidate
     const int rfk = fk - c0, rck = ck - c0;
-    bool bad = over;
+    unsigned bad = over ? 32u : 0u;                           // reason 32: more than CAND_CAP candidates on a line
     float thr = 0.f;
     if (!h->quirk[side]) {
-        if (rfk < 0 || rck >= cnt || rfk > rck) bad = true;
+        if (rfk < 0 || rck >= cnt || rfk > rck) bad |= 64u;   // reason 64: ranks not inside the candidate set
         // rank by counting (cnt <= 32): the candidate whose rank is rfk / rck publishes its item
         for (int p = sub; p < cnt; p += 8) {
             const float v = s_item[grp][p];
@@ -624,7 +625,7 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
             // every excluded cell below the candidate zone has exact item < (lo - EPS) units, every excluded cell
             // above it has exact item >= (lo + w + EPS) units: the selected order statistics must sit between
             const double lo_e = (double)(lo - EPS) * unit, hi_e = (double)(lo + w + EPS) * unit;
-            if ((double)ifk < lo_e || (double)ick >= hi_e) bad = true;
+            if ((double)ifk < lo_e || (double)ick >= hi_e) bad |= 128u;   // reason 128: order statistic outside its zone
             const float sfk = __fsqrt_rn(ifk), sck = __fsqrt_rn(ick);
             const float kf = h->kf[side];
             const float fkf = floorf(kf), ckf = ceilf(kf);
@@ -633,12 +634,12 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
             // cells emitted as certainly-in have exact item < (lo - EPS): their d must be <= thr;
             // cells dropped as certainly-out have exact item >= (lo + w + EPS): their d must be > thr
             const double t2 = (double)thr * (double)thr;
-            if (lo_e > 0.0 && t2 < lo_e * (1.0 + 1e-6)) bad = true;
-            if (t2 >= hi_e * (1.0 - 1e-6)) bad = true;
+            if (lo_e > 0.0 && t2 < lo_e * (1.0 + 1e-6)) bad |= 256u;   // reason 256/512: threshold not between the certain sets
+            if (t2 >= hi_e * (1.0 - 1e-6)) bad |= 512u;
         }
     }
     if (sub == 0) {
-        if (bad) atomicOr(&status[k], PAIR_ST_FALLBACK);
+        if (bad) atomicOr(&status[k], PAIR_ST_FALLBACK | bad);
         if (isrow) thr_q_all[(int64_t)slot * L.max_rows + idx] = thr;
         else thr_r_all[(int64_t)slot * L.max_cols + idx] = thr;
     }

@@ -168,4 +168,4 @@ class Engine:
         st = np.zeros(8, dtype=np.int64)
         check(self._lib.acoss_last_stats(self._ctx, st.ctypes.data))
         return dict(pairs=int(st[0]), fallback_pairs=int(st[1]), launches=int(st[2]), cells=int(st[3]),
-                    exact_cells=int(st[4]))
+                    exact_cells=int(st[4]), status_or=int(st[5]))
