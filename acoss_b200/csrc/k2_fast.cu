@@ -32,6 +32,7 @@ constexpr int HALO = M9 - 1;        // owned columns a strip recomputes (8)
 constexpr int NBIN = 64;            // histogram bins per level (+1 overflow row)
 constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
 constexpr int CAND_CAP = 64;        // candidates per row / column
+constexpr int BRACKET_TARGET = 40;  // a bracket holding more cells than this is split by another histogram level
 constexpr int WPC = 4;              // warps per CTA in the sweep kernels
 constexpr int RCV = 4;              // owned frames per lane (register columns) in the sweep kernels
 
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
     int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
     for (int i = threadIdx.x; i < L.lines; i += blockDim.x) {
         const int side = (i < L.max_rows) ? 0 : 1;
-        if (quirk2[side]) { lo[i] = 0; w[i] = 0; cb[i] = 0; sh[i] = 0; }
+        if (quirk2[side]) { lo[i] = 0; w[i] = 0; cb[i] = 0; sh[i] = -1; }
         else { lo[i] = lo1; w[i] = 0; cb[i] = 0; sh[i] = sh1; }
     }
     for (int i = threadIdx.x; i < Mx; i += blockDim.x) rowpack[i] = make_int4(aai[i], -2 * EPS, 4 * EPS, 0);
@@ -322,17 +323,25 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
     int32_t *cb_a = slot_ptr<int32_t>(scratch, L, slot, L.off_cb) + line0;
     int32_t *sh_a = slot_ptr<int32_t>(scratch, L, slot, L.off_sh) + line0;
 
-    SW sw;
-    sw.init(Y, nY, cb, lane, magic);
+    // a line is live at this level while its bracket still holds more than BRACKET_TARGET cells and can be
+    // split further (shift >= 0 in sh_a; -1 = done).  LEVEL 1 sees every line; refine levels skip strips
+    // with nothing left to do, so the third / fourth level cost nothing on ordinary pairs.
     int ynrel[RC], shf[RC];
     bool valid[RC];
+    bool work = false;
 #pragma unroll
     for (int kk = 0; kk < RC; ++kk) {
         const int j = cb + RC * lane + kk - HALO;            // owned window of this register column
         valid[kk] = (j >= cb) && (j < My) && (j < cb + SW::OUTW);
-        ynrel[kk] = valid[kk] ? yn[j] - lo_a[j] : 0x40000000;  // invalid columns land in the overflow bin
-        shf[kk] = valid[kk] ? sh_a[j] : 0;
+        const int shv = valid[kk] ? sh_a[j] : -1;
+        if (shv < 0) valid[kk] = false;
+        ynrel[kk] = valid[kk] ? yn[j] - lo_a[j] : 0x40000000;  // idle columns land in the overflow bin
+        shf[kk] = valid[kk] ? shv : 0;
+        work |= valid[kk];
     }
+    if (LEVEL > 1 && !__any_sync(0xffffffffu, work)) return;
+    SW sw;
+    sw.init(Y, nY, cb, lane, magic);
     uint32_t *hist = s_hist + (size_t)warp * (NBIN + 1) * HW * 32 + lane;
 #pragma unroll 1
     for (int b = 0; b < (NBIN + 1) * HW; ++b) hist[b * 32] = 0u;
@@ -369,22 +378,20 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
             atomicOr(&status[k], PAIR_ST_FALLBACK | 4u);      // reason 4: rank outside the binned range
             continue;
         }
-        if (LEVEL == 1) {
-            const long long range = (long long)(b2 - b1 + 1) << sh;
-            int sh2 = 0;
-            while ((range >> sh2) > NBIN) ++sh2;
-            lo_a[j] = lo + (b1 << sh);
-            sh_a[j] = sh2;
-            cb_a[j] = cb1;
-        } else {
-            lo_a[j] = lo + (b1 << sh);
-            w_a[j] = (b2 - b1 + 1) << sh;
-            cb_a[j] = cb1;
-            if (cend - cb1 > CAND_CAP - 8) atomicOr(&status[k], PAIR_ST_FALLBACK | 8u);   // reason 8: bracket too crowded (ties)
-            if (ORIENT == 1) {
-                int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
-                rowpack[j] = make_int4(yn[j], lo + (b1 << sh) - 2 * EPS, ((b2 - b1 + 1) << sh) + 4 * EPS, 0);
-            }
+        // new bracket = bins b1..b2; split it again next level unless it is small enough or cannot shrink
+        const int nlo = lo + (b1 << sh);
+        const long long range = (long long)(b2 - b1 + 1) << sh;
+        int sh2 = 0;
+        while ((range >> sh2) > NBIN) ++sh2;
+        // level 1 bins are coarse: split them unless the bracket is already tiny; later levels stop at BRACKET_TARGET
+        const bool done = (cend - cb1 <= (LEVEL == 1 ? 6 : BRACKET_TARGET)) || (sh == 0);
+        lo_a[j] = nlo;
+        w_a[j] = (int)range;
+        cb_a[j] = cb1;
+        sh_a[j] = done ? -1 : sh2;
+        if (ORIENT == 1) {
+            int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
+            rowpack[j] = make_int4(yn[j], nlo - 2 * EPS, (int)range + 4 * EPS, 0);
         }
     }
 }
@@ -718,10 +725,14 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
         attr_done = true;
     }
     const unsigned gc = (unsigned)(((int64_t)n * strips_c + WPC - 1) / WPC), gr = (unsigned)(((int64_t)n * strips_r + WPC - 1) / WPC);
+    // level 1 bins the whole item range, levels 2..4 split the bracket again (64x each); a level returns
+    // immediately for strips whose brackets are already small
     fast_hist_kernel<RC, 0, 1><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status);
-    fast_hist_kernel<RC, 0, 2><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status);
+    for (int lvl = 2; lvl <= 4; ++lvl)
+        fast_hist_kernel<RC, 0, 2><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status);
     fast_hist_kernel<RC, 1, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status);
-    fast_hist_kernel<RC, 1, 2><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status);
+    for (int lvl = 2; lvl <= 4; ++lvl)
+        fast_hist_kernel<RC, 1, 2><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status);
     CUDA_TRY(cudaGetLastError());
     fast_emit_kernel<RC><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
     CUDA_TRY(cudaGetLastError());
@@ -734,7 +745,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     fast_resolve_bits_kernel<<<dim3((lines * CAND_CAP + 255) / 256, n), 256, 0, st>>>(n, L, base, thr_q, thr_r, crp, g.words,
                                                                                       g.crp_words);
     CUDA_TRY(cudaGetLastError());
-    if (launches) *launches += 10;
+    if (launches) *launches += 14;
     return ACOSS_OK;
 }
 
