@@ -77,7 +77,7 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.strips_c = (g.max_cols + (32 * RCV - HALO) - 1) / (32 * RCV - HALO);
     L.slist_cap = 4096;                                   // uncertain cells one emit strip may record
     while (L.slist_cap < 3 * g.max_rows) L.slist_cap *= 2;
-    L.off_slist = take((size_t)L.strips_c * L.slist_cap * 4);
+    L.off_slist = take((size_t)L.strips_c * L.slist_cap * 12);      // 3 words per uncertain cell
     L.off_scnt = take((size_t)L.strips_c * 4);
     L.slot_bytes = align_up(o, 256);
     return L;
@@ -396,24 +396,6 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
     }
 }
 
-// Rare path of the emit sweep, kept out of line so the sweep loop stays small: lanes with c set append
-// one entry each to the strip-private list (warp-aggregated positions, no atomics).
-//   entry = i | j << 14 | row-zone << 28 | below-row-bracket << 29 | col-zone << 30 | below-col-bracket << 31
-__device__ __noinline__ unsigned emit_append(uint32_t *__restrict__ slist, unsigned nlist, unsigned cap, bool c, int ar, int ac,
-                                             int zp, int rw1, int cw1, int i, int j) {
-    const unsigned m = __ballot_sync(0xffffffffu, c);
-    if (c) {
-        const bool zz = zp < 0;                                 // z < 2 EPS
-        const bool rz = ((ar | (rw1 - ar)) >= 0) || zz;
-        const bool cz = (ac | (cw1 - ac)) >= 0;
-        const unsigned pos = nlist + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
-        if (pos < cap)
-            slist[pos] = (unsigned)i | ((unsigned)j << 14) | (rz ? 1u << 28 : 0u) | ((rz && ar < 2 * EPS) ? 1u << 29 : 0u) |
-                         (cz ? 1u << 30 : 0u) | ((cz && ac < 2 * EPS) ? 1u << 31 : 0u);
-    }
-    return nlist + __popc(m);
-}
-
 // ------------------------------------------------------------------------------------------------
 // emit sweep (orientation 0: owned = reference columns, streamed = query rows)
 // ------------------------------------------------------------------------------------------------
@@ -442,7 +424,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
     const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
     const int32_t *lo_c = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + L.max_rows;
     const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
-    uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * L.slist_cap;
+    uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * L.slist_cap * 3;
     unsigned nlist = 0u;
     uint32_t *crp = crp_all + (int64_t)slot * crp_words;
 
@@ -469,7 +451,14 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
 #pragma unroll
     for (int kk = 0; kk < RC; ++kk) bitk[kk] = (lword >= 0) ? (1u << (lbit + kk)) : 0u;
     const unsigned full = __activemask();                     // all 32 lanes (kept in a register)
-    uint32_t *rowp = crp + (cb >> 5) + ((lane < NW) ? lane : 0);   // advances by `words` per row
+    // lanes that feed the same CRP word form a group; the lowest lane of each group owns the store
+    const unsigned gmask = __match_any_sync(full, lword);
+    const bool gleader = (lword >= 0) && ((gmask & ((1u << lane) - 1u)) == 0u);
+    uint32_t *rowp = crp + (cb >> 5) + (lword >= 0 ? lword : 0);    // advances by `words` per row
+    const unsigned ltmask = (1u << lane) - 1u;
+    unsigned ij[RC];                                          // column part of a candidate entry
+#pragma unroll
+    for (int kk = 0; kk < RC; ++kk) ij[kk] = (unsigned)jcol[kk] << 14;
     const int nrows = nX - 1;
     // Per cell, with z the fixed-point item (sign-bit arithmetic, no predicates):
     //   ar = z - (rowLo - 2 EPS), ac = z - (colLo - 2 EPS), zp = z - 2 EPS
@@ -478,33 +467,43 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
     //   uncertain     <=> row zone or column zone or zp < 0 (near-zero item, so F7's NaN is caught exactly)
     run_sweep<RC, int4>(sw, X, rowpack, nrows, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
         const int xr = rp.x - rp.y, xp = rp.x - 2 * EPS, rw1 = rp.z - 1;
-        int ar[RC], ac[RC], zp[RC], ns[RC];
+        int ar[RC], ac[RC], ns[RC];
         unsigned v = 0u;
         int nsall = -1;
 #pragma unroll
         for (int kk = 0; kk < RC; ++kk) {
             ar[kk] = xr + ynv[kk] - sw.T[kk];
             ac[kk] = rp.x + ycl[kk] - sw.T[kk];
-            zp[kk] = xp + ynv[kk] - sw.T[kk];
+            const int zp = xp + ynv[kk] - sw.T[kk];
             const int zr = ar[kk] | (rw1 - ar[kk]), zc = ac[kk] | (cw1[kk] - ac[kk]);
-            ns[kk] = zr & zc & ~zp[kk];                        // sign set <=> NOT uncertain
+            ns[kk] = zr & zc & ~zp;                            // sign set <=> NOT uncertain
             nsall &= ns[kk];
-            v |= (unsigned)((ar[kk] & ac[kk] & ~zp[kk]) >> 31) & bitk[kk];
+            v |= (unsigned)((ar[kk] & ac[kk] & ~zp) >> 31) & bitk[kk];
         }
+        // one full-warp REDUX.OR per CRP word the strip row can touch (a partitioned REDUX is slower)
         unsigned wv = 0u;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             const unsigned ww = __reduce_or_sync(full, lword == w ? v : 0u);
-            wv = (lane == w) ? ww : wv;
+            wv = (lword == w) ? ww : wv;
         }
-        if (lane < NW && wv) atomicOr(rowp, wv);
+        if (gleader && wv) atomicOr(rowp, wv);
         rowp += words;
         if (__any_sync(full, nsall >= 0)) {
-            const int i = a - HALO;                           // query window (CRP row); i < Mx by construction
+            // uncertain cells: raw (i | j << 14, ar, ac) triples appended to the strip-private list with
+            // warp-aggregated positions; fast_scatter_kernel classifies them
+            const unsigned i = (unsigned)(a - HALO);          // query window (CRP row); i < Mx by construction
 #pragma unroll
-            for (int kk = 0; kk < RC; ++kk)
-                if (__any_sync(full, ns[kk] >= 0))
-                    nlist = emit_append(slist, nlist, (unsigned)L.slist_cap, ns[kk] >= 0, ar[kk], ac[kk], zp[kk], rw1, cw1[kk], i, jcol[kk]);
+            for (int kk = 0; kk < RC; ++kk) {
+                const bool c = ns[kk] >= 0;
+                const unsigned m = __ballot_sync(full, c);
+                const unsigned pos = nlist + __popc(m & ltmask);
+                if (c && pos < (unsigned)L.slist_cap) {
+                    uint32_t *e = slist + (size_t)pos * 3;
+                    e[0] = i | ij[kk]; e[1] = (uint32_t)ar[kk]; e[2] = (uint32_t)ac[kk];
+                }
+                nlist += __popc(m);
+            }
         }
     });
     (void)Mx;
@@ -522,20 +521,28 @@ __global__ void __launch_bounds__(128) fast_scatter_kernel(int n, FastLayout L, 
     const uint32_t cntv = slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[strip];
     if (cntv > (uint32_t)L.slist_cap && threadIdx.x == 0) atomicOr(&status[first + slot], PAIR_ST_FALLBACK | 16u);   // reason 16: strip list overflow
     const uint32_t m = min(cntv, (uint32_t)L.slist_cap);
-    const uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * L.slist_cap;
+    const uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * L.slist_cap * 3;
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
+    const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
+    const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
     for (uint32_t e = threadIdx.x; e < m; e += blockDim.x) {
-        const uint32_t v = slist[e];
+        const uint32_t v = slist[e * 3];
+        const int ar = (int)slist[e * 3 + 1], ac = (int)slist[e * 3 + 2];   // z - (rowLo - 2 EPS), z - (colLo - 2 EPS)
         const int i = v & 0x3fff, j = (v >> 14) & 0x3fff;
-        if (v & (1u << 28)) {
+        const int4 rp = rowpack[i];                           // {aa_fix, rowLo - 2 EPS, rowW + 4 EPS, -}
+        const int z = ar + rp.y;
+        const bool zz = z < 2 * EPS;                          // near-zero item: always evaluated exactly
+        const bool rz = (ar >= 0 && ar < rp.z) || zz;
+        const bool cz = ac >= 0 && ac < w_c[j] + 4 * EPS;
+        if (rz) {
             const unsigned p = atomicAdd(&cnt[i], 1u);
-            if (p < CAND_CAP) cand[(size_t)i * CAND_CAP + p] = (uint16_t)(j | ((v >> 29) & 1u) << 15);
+            if (p < CAND_CAP) cand[(size_t)i * CAND_CAP + p] = (uint16_t)(j | (ar < 2 * EPS ? 0x8000 : 0));
         }
-        if (v & (1u << 30)) {
+        if (cz) {
             const int line = L.max_rows + j;
             const unsigned p = atomicAdd(&cnt[line], 1u);
-            if (p < CAND_CAP) cand[(size_t)line * CAND_CAP + p] = (uint16_t)(i | ((v >> 31) & 1u) << 15);
+            if (p < CAND_CAP) cand[(size_t)line * CAND_CAP + p] = (uint16_t)(i | (ac < 2 * EPS ? 0x8000 : 0));
         }
     }
 }
