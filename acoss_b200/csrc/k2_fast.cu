@@ -206,12 +206,14 @@ struct Sweep {
     __device__ __forceinline__ void dot(const float4 &x0, const float4 &x1, const float4 &x2, int (&eb)[RC]) const {
 #pragma unroll
         for (int k = 0; k < RC; ++k) {
-            float acc = __fmul_rn(x0.x, y[k][0]);
+            // the chain starts at the magic constant, so every partial sum already sits in the fixed-point
+            // binade (12 roundings of at most half a unit each: inside the EPS budget)
+            float acc = __fmaf_rn(x0.x, y[k][0], magic);
             acc = __fmaf_rn(x0.y, y[k][1], acc); acc = __fmaf_rn(x0.z, y[k][2], acc); acc = __fmaf_rn(x0.w, y[k][3], acc);
             acc = __fmaf_rn(x1.x, y[k][4], acc); acc = __fmaf_rn(x1.y, y[k][5], acc); acc = __fmaf_rn(x1.z, y[k][6], acc);
             acc = __fmaf_rn(x1.w, y[k][7], acc); acc = __fmaf_rn(x2.x, y[k][8], acc); acc = __fmaf_rn(x2.y, y[k][9], acc);
             acc = __fmaf_rn(x2.z, y[k][10], acc); acc = __fmaf_rn(x2.w, y[k][11], acc);
-            eb[k] = __float_as_int(__fadd_rn(acc, magic));
+            eb[k] = __float_as_int(acc);
         }
     }
 
@@ -552,10 +554,16 @@ __global__ void __launch_bounds__(128) fast_scatter_kernel(int n, FastLayout L, 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float exact_item(const float *__restrict__ Q, const float *__restrict__ R, int i, int j,
                                             float aa, float bb) {
-    const float *a = Q + (int64_t)i * NBINS, *b = R + (int64_t)j * NBINS;     // 9 consecutive frames each
+    // 9 consecutive frames of each side = 108 floats = 27 float4 (frames are 48 B, bases 16 B aligned)
+    const float4 *a = reinterpret_cast<const float4 *>(Q + (int64_t)i * NBINS);
+    const float4 *b = reinterpret_cast<const float4 *>(R + (int64_t)j * NBINS);
     double acc = 0.0;
-#pragma unroll 4
-    for (int t = 0; t < M9 * NBINS; ++t) acc = acc_f32prod(acc, a[t], b[t]);
+#pragma unroll 3
+    for (int t = 0; t < M9 * NBINS / 4; ++t) {
+        const float4 u = __ldg(a + t), v = b[t];
+        acc = acc_f32prod(acc, u.x, v.x); acc = acc_f32prod(acc, u.y, v.y);
+        acc = acc_f32prod(acc, u.z, v.z); acc = acc_f32prod(acc, u.w, v.w);
+    }
     return __fadd_rn(__fsub_rn(aa, __fmul_rn(2.f, (float)acc)), bb);
 }
 
@@ -668,14 +676,14 @@ __global__ void __launch_bounds__(256) fast_resolve_bits_kernel(int n, FastLayou
     if (slot >= n) return;
     const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
     const int Mx = h->Mx, Nx = h->Nx;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;      // (line, position)
-    const int gline = t / CAND_CAP, p = t % CAND_CAP;
+    const int gline = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;   // 16 lanes per line
+    const int sub = threadIdx.x & 15;
     if (gline >= Mx + Nx) return;
     const bool isrow = gline < Mx;
     const int idx = isrow ? gline : gline - Mx;
     const int line = isrow ? idx : L.max_rows + idx;
-    const uint32_t cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt)[line];
-    if ((unsigned)p >= min(cnt, (unsigned)CAND_CAP)) return;
+    const int cnt = (int)min(slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt)[line], (uint32_t)CAND_CAP);
+    for (int p = sub; p < cnt; p += 16) {
     const unsigned e = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand)[(size_t)line * CAND_CAP + p];
     const float d = slot_ptr<float>(scratch, L, slot, L.off_candd)[(size_t)line * CAND_CAP + p];
     const int other = e & 0x7fff;
@@ -683,6 +691,7 @@ __global__ void __launch_bounds__(256) fast_resolve_bits_kernel(int n, FastLayou
     const float tq = thr_q_all[(int64_t)slot * L.max_rows + i], tr = thr_r_all[(int64_t)slot * L.max_cols + j];
     if ((__fsub_rn(tq, d) >= 0.f) && (__fsub_rn(tr, d) >= 0.f))
         atomicOr(crp_all + (int64_t)slot * crp_words + (int64_t)i * words + (j >> 5), 1u << (j & 31));
+    }
 }
 
 __global__ void collect_fallback_kernel(const uint32_t *__restrict__ status, int64_t first, int n,
@@ -749,7 +758,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     fast_resolve_thr_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(ts, pairs, first, n, L, base, p.integer_guard, unit,
                                                                        thr_q, thr_r, status);
     CUDA_TRY(cudaGetLastError());
-    fast_resolve_bits_kernel<<<dim3((lines * CAND_CAP + 255) / 256, n), 256, 0, st>>>(n, L, base, thr_q, thr_r, crp, g.words,
+    fast_resolve_bits_kernel<<<dim3((lines * 16 + 255) / 256, n), 256, 0, st>>>(n, L, base, thr_q, thr_r, crp, g.words,
                                                                                       g.crp_words);
     CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 14;
