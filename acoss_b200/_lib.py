@@ -53,6 +53,7 @@ SIGNATURES = {
     "acoss_dp_bytes": (C.c_int, [_vp, _vp, _i64p, _i32p, C.c_int64, C.c_int32, C.c_float, C.c_float, _fp]),
     "acoss_knn_sw": (C.c_int, [_vp, _vp, _i64p, _i32p, _i32p, C.c_int64, _fp, _vp]),
     "acoss_last_stats": (C.c_int, [_vp, _i64p]),
+    "acoss_debug_counters": (C.c_int, [_vp, _i64p]),
     "acoss_set_profiling": (C.c_int, [_vp, C.c_int]),
     "acoss_stage_ms": (C.c_int, [_vp, _vp]),
 }

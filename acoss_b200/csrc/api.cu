@@ -42,8 +42,9 @@ struct acoss_ctx {
     int32_t fx_exp = -1000, nonneg = 0;
     int64_t ws_limit = (int64_t)24 << 30;
     // grow-only scratch
-    Buf pairs, scores, oti, status, crp, rows, cols, thr_q, thr_r, rrot, aa, bb, D, halo, misc, fast, fbmap;
+    Buf pairs, scores, oti, status, crp, rows, cols, thr_q, thr_r, rrot, aa, bb, D, halo, misc, fast, fbmap, dbg;
     uint32_t *h_flag = nullptr;   // pinned
+    uint32_t *h_dbg = nullptr;    // pinned, 32 diagnostic counters
     int64_t stats[8] = {0};
     int pending_status_check = 0;
     int stats_reason_pending = 0;
@@ -140,6 +141,8 @@ int acoss_create(acoss_ctx **out, int device) {
     c->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMallocHost((void **)&c->h_flag, 64));
+    CUDA_TRY(cudaMallocHost((void **)&c->h_dbg, 128));
+    memset(c->h_dbg, 0, 128);
     *out = c;
     return ACOSS_OK;
 }
@@ -151,12 +154,13 @@ int acoss_destroy(acoss_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Buf *bufs[] = {&c->pairs, &c->scores, &c->oti, &c->status, &c->crp, &c->rows, &c->cols, &c->thr_q, &c->thr_r,
-                   &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap};
+                   &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap, &c->dbg};
     for (Buf *b : bufs) free_buf(*b);
     if (c->own_frames && c->d_frames) cudaFree(c->d_frames);
     if (c->d_offsets) cudaFree(c->d_offsets);
     if (c->d_gchroma) cudaFree(c->d_gchroma);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->h_dbg) cudaFreeHost(c->h_dbg);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -290,6 +294,8 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     TRY(ensure(c->misc, 256));
     CUDA_TRY(cudaMemsetAsync(c->status.p, 0, (size_t)K * 4 + 64, st));
     CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 256, st));
+    TRY(ensure(c->dbg, 128));
+    CUDA_TRY(cudaMemsetAsync(c->dbg.p, 0, 128, st));
     {
         StageTimer t1(c, 0);
         TRY(launch_oti(ts, pairs_dev, K, p->noti, p->oti, (int32_t *)c->oti.p, st));
@@ -332,7 +338,7 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
         StageTimer t2(c, 1);
         if (fast) {
             TRY(launch_k2_fast(ts, pairs_dev, (const int32_t *)c->oti.p, first, n, *p, g, c->fast.p, fast_slot,
-                               (uint32_t *)c->crp.p, (float *)c->thr_q.p, (float *)c->thr_r.p, status, st, &launches));
+                               (uint32_t *)c->crp.p, (float *)c->thr_q.p, (float *)c->thr_r.p, status, (uint32_t *)c->dbg.p, st, &launches));
             // exact fallback for pairs the fast path flagged: compact their slot ids, re-run in groups
             TRY(ensure(c->fbmap, (size_t)slots * 4 + 64));
             int nfb = 0;
@@ -379,6 +385,7 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     CUDA_TRY(cudaGetLastError());
     ++launches;
     CUDA_TRY(cudaMemcpyAsync(c->h_flag, c->misc.p, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_dbg, c->dbg.p, 128, cudaMemcpyDeviceToHost, st));
     c->pending_status_check = 1;
     c->pending_pairs = K;
     c->stats[0] = K;
@@ -563,6 +570,12 @@ int acoss_knn_sw(acoss_ctx *c, const double *csms, const int64_t *offsets, const
     cleanup();
 #undef TRYC
 #undef CUDA_TRYC
+    return ACOSS_OK;
+}
+
+int acoss_debug_counters(acoss_ctx *c, int64_t out[32]) {
+    if (!c || !out) { acoss_set_error("debug_counters: NULL argument"); return ACOSS_E_INVALID; }
+    for (int i = 0; i < 32; ++i) out[i] = c->h_dbg ? (int64_t)c->h_dbg[i] : 0;
     return ACOSS_OK;
 }
 

@@ -23,13 +23,17 @@
 //    essentia's percentile formula and patch the candidate bits.  Consistency checks that make
 //    the certain/uncertain split provably exact are evaluated per row/column; a pair that fails
 //    one is flagged and re-run by k2_exact.cu.
+#include <stdlib.h>
+
 #include "k2_fast.cuh"
 
 namespace {
 
 constexpr int M9 = 9;               // frameStackSize handled by this path
 constexpr int HALO = M9 - 1;        // owned columns a strip recomputes (8)
-constexpr int NBIN = 64;            // histogram bins per level (+1 overflow row)
+constexpr int NBIN = 64;            // histogram bins per level (+ one underflow and one overflow row)
+constexpr int SPARSE_CAP = 512;     // live lines per pair and orientation the sparse refinement can take
+constexpr int SBIN = 256;           // bins of the per-line sample histogram (select kernel)
 constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
 constexpr int CAND_CAP = 64;        // candidates per row / column
 constexpr int BRACKET_TARGET = 40;  // a bracket holding more cells than this is split by another histogram level
@@ -41,15 +45,18 @@ struct PairHdr {                    // per-slot header written by fast_prep_kern
     int32_t fk[2], ck[2];           // 0-based ranks floor(k), ceil(k): [0] rows (L = Nx), [1] columns (L = Mx)
     int32_t quirk[2];               // 1: threshold is forced to 0 (integer k without guard, F1)
     float kf[2];                    // fractional rank (float32, essentia arithmetic)
-    int32_t lo1, sh1;               // level-1 histogram origin / shift
-    int32_t pad[2];
+    int32_t lo1, sh1;               // origin of the pair's item range (fixed point) / shift of a 64-bin split of it
+    int32_t hi1;                    // end of the pair's item range
+    int32_t pad;
 };
 
 struct FastLayout {
     size_t slot_bytes;
     size_t off_hdr, off_rrot, off_aaf, off_bbf, off_aai, off_bbi, off_lo, off_w, off_cb, off_sh, off_cnt,
-        off_cand, off_candd, off_rowpack, off_slist, off_scnt;
+        off_cand, off_candd, off_rowpack, off_slist, off_scnt, off_samp_r, off_samp_c, off_live, off_nlive;
     int max_rows, max_cols, max_frames, lines, strips_c, slist_cap;
+    int slog;                           // log2 of the diagonal sampling stride S
+    int nst_r, nst_c;                   // sample slots per row (ceil(max_cols / S)) / per column
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -79,6 +86,20 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     while (L.slist_cap < 3 * g.max_rows) L.slist_cap *= 2;
     L.off_slist = take((size_t)L.strips_c * L.slist_cap * 12);      // 3 words per uncertain cell
     L.off_scnt = take((size_t)L.strips_c * 4);
+    // diagonal sampling stride: the bracket a line gets from n_s samples holds ~2.35 L / sqrt(n_s) cells, which
+    // the 64-bin split must bring under BRACKET_TARGET  =>  n_s >= (0.003 L)^2, S = L / n_s <= 1 / (9e-6 L)
+    {
+        const int Lmax = g.max_rows > g.max_cols ? g.max_rows : g.max_cols;
+        const double smax = 1.0 / (9e-6 * (double)(Lmax > 1 ? Lmax : 1));
+        L.slog = 5;
+        while (L.slog > 2 && (double)(1 << L.slog) > smax) --L.slog;
+    }
+    L.nst_r = ((g.max_cols - 1) >> L.slog) + 1;
+    L.nst_c = ((g.max_rows - 1) >> L.slog) + 1;
+    L.off_samp_r = take((size_t)L.nst_r * g.max_rows * 4);      // [t = j / S][i]
+    L.off_samp_c = take((size_t)L.nst_c * g.max_cols * 4);      // [t = i / S][j]
+    L.off_live = take((size_t)2 * SPARSE_CAP * 4);              // [side][SPARSE_CAP] lines still live after the dense level
+    L.off_nlive = take(8);
     L.slot_bytes = align_up(o, 256);
     return L;
 }
@@ -113,6 +134,7 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     for (int i = threadIdx.x; i < L.lines; i += blockDim.x) cnt[i] = 0u;
     for (int i = threadIdx.x; i < L.strips_c; i += blockDim.x) slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[i] = 0u;
+    if (threadIdx.x < 2) slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive)[threadIdx.x] = 0u;
     __syncthreads();
     float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
     int32_t *aai = slot_ptr<int32_t>(scratch, L, slot, L.off_aai), *bbi = slot_ptr<int32_t>(scratch, L, slot, L.off_bbi);
@@ -136,10 +158,8 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
     __syncthreads();
     PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
     int lo1 = -2 * EPS, sh1 = 0;
-    {
-        const long long range = (long long)s_max[0] + s_max[1] + 4 * EPS + 1;
-        while ((range >> sh1) > NBIN - 1) ++sh1;
-    }
+    const long long range1 = (long long)s_max[0] + s_max[1] + 4 * EPS + 1;
+    while ((range1 >> sh1) > NBIN - 1) ++sh1;
     int fk2[2], ck2[2], quirk2[2];
     float kf2[2];
     for (int o = 0; o < 2; ++o) {
@@ -152,7 +172,7 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
     if (threadIdx.x == 0) {
         h->nq = nq; h->nr = nr; h->Mx = Mx; h->Nx = Nx;
         for (int o = 0; o < 2; ++o) { h->fk[o] = fk2[o]; h->ck[o] = ck2[o]; h->quirk[o] = quirk2[o]; h->kf[o] = kf2[o]; }
-        h->lo1 = lo1; h->sh1 = sh1;
+        h->lo1 = lo1; h->sh1 = sh1; h->hi1 = lo1 + (int)range1;
     }
     // level-1 bracket state for every line; emit-ready defaults for quirk sides (threshold 0)
     int32_t *lo = slot_ptr<int32_t>(scratch, L, slot, L.off_lo), *w = slot_ptr<int32_t>(scratch, L, slot, L.off_w);
@@ -164,6 +184,145 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
         else { lo[i] = lo1; w[i] = 0; cb[i] = 0; sh[i] = sh1; }
     }
     for (int i = threadIdx.x; i < Mx; i += blockDim.x) rowpack[i] = make_int4(aai[i], -2 * EPS, 4 * EPS, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagonal sampler: fixed-point items of the cells (i, j) with (j - i) % S == 0, i.e. every S-th
+// diagonal.  A warp covers 24 consecutive positions of KD such diagonals: lane l computes the
+// frame-level dot product of position i0 + l, the 9-tap window sum runs across lanes (4 shuffles).
+// Every sample is a sample of its row and of its column: samp_r[j / S][i], samp_c[i / S][j].
+// These samples only steer the histogram brackets (select kernel below); exactness never depends
+// on them.
+// ------------------------------------------------------------------------------------------------
+constexpr int SKD = 4;              // diagonals per warp task
+constexpr int SPOS = 32 - HALO;     // window sums one warp pass produces per diagonal (24)
+
+__global__ void __launch_bounds__(128) fast_sample_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+                                                          int64_t first, int n, FastLayout L,
+                                                          char *__restrict__ scratch, int ngrp_max, int nblk_max,
+                                                          float magic) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t task = (int64_t)blockIdx.x * 4 + warp;
+    const int per_slot = ngrp_max * nblk_max;
+    const int slot = (int)(task / per_slot);
+    if (slot >= n) return;
+    const int rem = (int)(task - (int64_t)slot * per_slot);
+    const int grp = rem / nblk_max, blk = rem - grp * nblk_max;
+    const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
+    if (h->quirk[0] && h->quirk[1]) return;
+    const int nq = h->nq, nr = h->nr, Mx = h->Mx, Nx = h->Nx;
+    const int slog = L.slog;
+    const int i0 = blk * SPOS;
+    if (i0 >= Mx) return;
+    // diagonals d = S * u, u in [-(Mx-1)/S, (Nx-1)/S]
+    const int u_lo = -((Mx - 1) >> slog);
+    const int u0 = u_lo + grp * SKD;
+    if (((int64_t)u0 << slog) > (int64_t)(Nx - 1) - i0) return;                       // block lies right of the matrix
+    if ((((int64_t)u0 + SKD - 1) << slog) + i0 + SPOS - 1 < 0) return;                // ... or left of it
+    const int64_t k = first + slot;
+    const int q = pairs[2 * k];
+    const float *Qf = ts.frames + ts.offsets[q] * NBINS;
+    const float *Rf = slot_ptr<float>(scratch, L, slot, L.off_rrot);
+    const int32_t *aai = slot_ptr<int32_t>(scratch, L, slot, L.off_aai), *bbi = slot_ptr<int32_t>(scratch, L, slot, L.off_bbi);
+    int32_t *samp_r = slot_ptr<int32_t>(scratch, L, slot, L.off_samp_r), *samp_c = slot_ptr<int32_t>(scratch, L, slot, L.off_samp_c);
+    const int i = i0 + lane;
+    const bool iok = lane < SPOS && i < Mx;
+    float x[NBINS];
+    {
+        const float4 *p = reinterpret_cast<const float4 *>(Qf + (int64_t)min(i, nq - 1) * NBINS);
+        const float4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+        x[0] = 2.f * v0.x; x[1] = 2.f * v0.y; x[2] = 2.f * v0.z; x[3] = 2.f * v0.w;
+        x[4] = 2.f * v1.x; x[5] = 2.f * v1.y; x[6] = 2.f * v1.z; x[7] = 2.f * v1.w;
+        x[8] = 2.f * v2.x; x[9] = 2.f * v2.y; x[10] = 2.f * v2.z; x[11] = 2.f * v2.w;
+    }
+    const int aa = iok ? aai[i] : 0;
+    const int mbits = __float_as_int(magic);
+#pragma unroll
+    for (int kd = 0; kd < SKD; ++kd) {
+        const int d = (u0 + kd) << slog;
+        const int j = i + d;
+        const float4 *p = reinterpret_cast<const float4 *>(Rf + (int64_t)min(max(j, 0), nr - 1) * NBINS);
+        const float4 y0 = p[0], y1 = p[1], y2 = p[2];
+        float acc = __fmaf_rn(x[0], y0.x, magic);
+        acc = __fmaf_rn(x[1], y0.y, acc); acc = __fmaf_rn(x[2], y0.z, acc); acc = __fmaf_rn(x[3], y0.w, acc);
+        acc = __fmaf_rn(x[4], y1.x, acc); acc = __fmaf_rn(x[5], y1.y, acc); acc = __fmaf_rn(x[6], y1.z, acc);
+        acc = __fmaf_rn(x[7], y1.w, acc); acc = __fmaf_rn(x[8], y2.x, acc); acc = __fmaf_rn(x[9], y2.y, acc);
+        acc = __fmaf_rn(x[10], y2.z, acc); acc = __fmaf_rn(x[11], y2.w, acc);
+        const int v = __float_as_int(acc) - mbits;
+        const int s1 = v + __shfl_down_sync(0xffffffffu, v, 1);
+        const int s2 = s1 + __shfl_down_sync(0xffffffffu, s1, 2);
+        const int s4 = s2 + __shfl_down_sync(0xffffffffu, s2, 4);
+        const int T = s4 + __shfl_down_sync(0xffffffffu, v, 8);
+        if (iok && j >= 0 && j < Nx) {
+            const int z = aa + bbi[j] - T;
+            samp_r[(int64_t)(j >> slog) * L.max_rows + i] = z;
+            samp_c[(int64_t)(i >> slog) * L.max_cols + j] = z;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// select: one thread per line.  A private 256-bin histogram of the line's samples (over the pair's
+// item range) gives the bins holding the sample ranks mu -+ 4.5 sigma of the wanted order statistic;
+// that is the line's first bracket [lo, lo + 64 << sh) for the histogram sweeps.  A wrong bracket
+// costs another sweep level, never a wrong result (under / overflow are counted exactly).
+// ------------------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 128;
+
+__global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(int n, FastLayout L, char *__restrict__ scratch) {
+    extern __shared__ uint32_t s_sel_hist[];                 // [SBIN / 2][SEL_THREADS], two 16-bit counters per word
+    const int slot = blockIdx.y;
+    if (slot >= n) return;
+    const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
+    const int Mx = h->Mx, Nx = h->Nx;
+    const int gline = blockIdx.x * SEL_THREADS + threadIdx.x;
+    if (blockIdx.x * SEL_THREADS >= Mx + Nx) return;
+    uint32_t *hist = s_sel_hist + threadIdx.x;
+#pragma unroll 4
+    for (int b = 0; b < SBIN / 2; ++b) hist[b * SEL_THREADS] = 0u;
+    if (gline >= Mx + Nx) return;
+    const bool isrow = gline < Mx;
+    const int idx = isrow ? gline : gline - Mx;
+    const int side = isrow ? 0 : 1;
+    if (h->quirk[side]) return;                               // threshold forced to 0: no selection on this side
+    const int line = isrow ? idx : L.max_rows + idx;
+    const int slog = L.slog, S = 1 << slog;
+    const int Lother = isrow ? Nx : Mx;                       // entries of the line
+    const int r0 = idx & (S - 1);                             // first sampled position along the line
+    const int ns = (r0 < Lother) ? ((Lother - 1 - r0) >> slog) + 1 : 0;
+    const int32_t *samp = isrow ? slot_ptr<int32_t>(scratch, L, slot, L.off_samp_r) : slot_ptr<int32_t>(scratch, L, slot, L.off_samp_c);
+    const int64_t pitch = isrow ? L.max_rows : L.max_cols;
+    const int lo1 = h->lo1, hi1 = h->hi1;
+    int shs = 0;
+    while ((((int64_t)hi1 - lo1) >> shs) > SBIN - 1) ++shs;
+    for (int t = 0; t < ns; ++t) {
+        const int z = samp[(int64_t)t * pitch + idx];
+        const int b = min(max((z - lo1) >> shs, 0), SBIN - 1);
+        hist[(b >> 1) * SEL_THREADS] += 1u << (16 * (b & 1));
+    }
+    // wanted ranks floor(k) .. ceil(k) of Lother entries -> sample ranks mu -+ 4.5 sigma
+    const float pq = ((float)h->fk[side] + 0.5f) / (float)Lother;
+    const float mu = pq * (float)ns, sg = sqrtf(fmaxf(mu * (1.f - pq), 0.25f));
+    const int r_lo = max((int)floorf(mu - 4.5f * sg) - 1, 0);
+    const int r_hi = (int)ceilf(mu + 4.5f * sg) + 1;
+    int cum = 0, b_lo = -1, b_hi = -1;
+    for (int b = 0; b < SBIN / 2; ++b) {
+        const uint32_t wv = hist[b * SEL_THREADS];
+        const int c0 = wv & 0xffff, c1 = wv >> 16;
+        if (b_lo < 0 && cum + c0 > r_lo) b_lo = 2 * b;
+        if (b_hi < 0 && cum + c0 > r_hi) b_hi = 2 * b;
+        cum += c0;
+        if (b_lo < 0 && cum + c1 > r_lo) b_lo = 2 * b + 1;
+        if (b_hi < 0 && cum + c1 > r_hi) b_hi = 2 * b + 1;
+        cum += c1;
+    }
+    int lo = lo1, hi = hi1;
+    if (b_lo >= 0) lo = lo1 + (b_lo << shs);
+    if (b_hi >= 0) hi = min(hi1, lo1 + ((b_hi + 1) << shs));
+    int sh = 0;
+    while ((((int64_t)hi - lo) >> sh) > NBIN) ++sh;
+    slot_ptr<int32_t>(scratch, L, slot, L.off_lo)[line] = lo;
+    slot_ptr<int32_t>(scratch, L, slot, L.off_sh)[line] = sh;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -288,17 +447,55 @@ __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bracket update shared by the dense and the sparse histogram levels.  hist[b * stride] (shifted / masked)
+// is the count of bin b: b = 0 items below the bracket, 1..NBIN its bins, NBIN + 1 items above.  The new
+// bracket is the run of bins holding ranks fk and ck (the under / overflow "bins" reach to the end of the
+// pair's item range, the next level splits them).
+// ------------------------------------------------------------------------------------------------
+struct Bracket {
+    int lo, w, below, sh;       // new origin, width, exact count of items below lo, shift of the next level
+    bool done, miss, bad;
+};
+
+template <int STRIDE>
+__device__ __forceinline__ Bracket split_bracket(const uint32_t *hp, int hs, uint32_t mask, int fk, int ck, int lo, int sh,
+                                                 int rlo, int rhi) {
+    int cum = 0, b1 = -2, b2 = -2, cb1 = 0, cend = 0;          // the underflow bin counts every item below the bracket
+    for (int b = 0; b < NBIN + 2; ++b) {                      // b - 1 = bin of the bracket; -1 under, NBIN over
+        const int c = (int)((hp[b * STRIDE] >> hs) & mask);
+        if (b1 < -1 && cum + c > fk) { b1 = b - 1; cb1 = cum; }
+        if (b2 < -1 && cum + c > ck) { b2 = b - 1; cend = cum + c; }
+        cum += c;
+    }
+    Bracket r;
+    r.bad = (b1 < -1 || b2 < -1);
+    const long long nlo = (b1 < 0) ? (long long)rlo : (long long)lo + ((long long)b1 << sh);
+    const long long nhi = (b2 >= NBIN) ? (long long)rhi : (b2 < 0) ? (long long)lo : (long long)lo + ((long long)(b2 + 1) << sh);
+    r.miss = (b1 < 0) || (b2 >= NBIN);
+    const long long range = (nhi > nlo) ? nhi - nlo : 1;
+    int sh2 = 0;
+    while ((range >> sh2) > NBIN) ++sh2;
+    // split again unless the bracket is small enough or cannot shrink
+    r.done = !r.miss && ((cend - cb1 <= BRACKET_TARGET) || (sh == 0));
+    r.lo = (int)nlo; r.w = (int)range; r.below = cb1; r.sh = sh2;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // histogram sweep.  ORIENT = 0: owned = reference columns (column thresholds), streamed = query.
 //                   ORIENT = 1: owned = query rows (row thresholds), streamed = rotated reference.
-// LEVEL = 1: coarse bins over the whole pair range -> per-line refined origin / shift.
-// LEVEL = 2: fine bins -> final bracket [lo, lo + w) holding ranks floor(k) and ceil(k).
+// Every live line enters with a bracket [lo, lo + 64 << sh) (first level: from the sample selection).  The
+// sweep counts the line's items into 64 bins of the bracket plus an underflow and an overflow bin, so the
+// position of the wanted ranks is known exactly whatever the bracket was: inside (bracket shrinks to the
+// bins holding floor(k) .. ceil(k)), below or above (bracket moves to that side of the pair's item range
+// and the next level splits it).
 // ------------------------------------------------------------------------------------------------
-template <int RC, int ORIENT, int LEVEL>
+template <int RC, int ORIENT>
 __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
-                                                             uint32_t *__restrict__ status) {
-    extern __shared__ uint32_t s_hist[];                      // [WPC][NBIN + 1][RC / 2][32], two 16-bit counters per word
+                                                             uint32_t *__restrict__ status, uint32_t *__restrict__ dbg) {
+    extern __shared__ uint32_t s_hist[];                      // [WPC][NBIN + 2][RC / 2][32], two 16-bit counters per word
     using SW = Sweep<RC>;
     static_assert(RC % 2 == 0, "histogram packing needs an even number of register columns");
     constexpr int HW = RC / 2;                                // words per (bin, lane)
@@ -325,9 +522,9 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
     int32_t *cb_a = slot_ptr<int32_t>(scratch, L, slot, L.off_cb) + line0;
     int32_t *sh_a = slot_ptr<int32_t>(scratch, L, slot, L.off_sh) + line0;
 
-    // a line is live at this level while its bracket still holds more than BRACKET_TARGET cells and can be
-    // split further (shift >= 0 in sh_a; -1 = done).  LEVEL 1 sees every line; refine levels skip strips
-    // with nothing left to do, so the third / fourth level cost nothing on ordinary pairs.
+    // a line is live while its bracket still holds more than BRACKET_TARGET cells and can be split further
+    // (shift >= 0 in sh_a; -1 = done).  Strips with nothing left to do return at once, so the extra levels
+    // cost nothing on ordinary pairs.
     int ynrel[RC], shf[RC];
     bool valid[RC];
     bool work = false;
@@ -337,65 +534,205 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
         valid[kk] = (j >= cb) && (j < My) && (j < cb + SW::OUTW);
         const int shv = valid[kk] ? sh_a[j] : -1;
         if (shv < 0) valid[kk] = false;
-        ynrel[kk] = valid[kk] ? yn[j] - lo_a[j] : 0x40000000;  // idle columns land in the overflow bin
         shf[kk] = valid[kk] ? shv : 0;
+        // bin index = ((z - lo) >> sh) + 1 clamped to [0, NBIN + 1]: 0 = below the bracket, NBIN + 1 = above
+        ynrel[kk] = valid[kk] ? yn[j] - lo_a[j] + (1 << shv) : 0x40000000;   // idle columns land in the overflow bin
         work |= valid[kk];
     }
-    if (LEVEL > 1 && !__any_sync(0xffffffffu, work)) return;
+    if (!__any_sync(0xffffffffu, work)) return;
+    int n_live = 0, n_miss = 0, n_left = 0;                  // diagnostics (acoss_debug_counters)
+#pragma unroll
+    for (int kk = 0; kk < RC; ++kk) n_live += valid[kk] ? 1 : 0;
     SW sw;
     sw.init(Y, nY, cb, lane, magic);
-    uint32_t *hist = s_hist + (size_t)warp * (NBIN + 1) * HW * 32 + lane;
+    uint32_t *hist = s_hist + (size_t)warp * (NBIN + 2) * HW * 32 + lane;
 #pragma unroll 1
-    for (int b = 0; b < (NBIN + 1) * HW; ++b) hist[b * 32] = 0u;
+    for (int b = 0; b < (NBIN + 2) * HW; ++b) hist[b * 32] = 0u;
     __syncwarp();
 
     const int nrows = nX - 1;                                 // streamed frames 0 .. nX-2 (F4: last frame unused)
     run_sweep<RC, int>(sw, X, xn, nrows, [&](int, int xb) {
 #pragma unroll
         for (int kk = 0; kk < RC; ++kk) {
-            const unsigned zr = (unsigned)(xb + ynrel[kk] - sw.T[kk]);
-            const unsigned idx = min(zr >> shf[kk], (unsigned)NBIN);
+            const int zr = xb + ynrel[kk] - sw.T[kk];
+            const int idx = __vimin_s32_relu(zr >> shf[kk], NBIN + 1);
             atomicAdd(&hist[(idx * HW + kk / 2) * 32], 1u << (16 * (kk & 1)));   // thread-private bank: conflict-free
         }
     });
     __syncwarp();
     // per-thread scan of its own columns' histograms
-    const int fk = h->fk[ORIENT == 0 ? 1 : 0], ck = h->ck[ORIENT == 0 ? 1 : 0];
+    const int side = (ORIENT == 0) ? 1 : 0;
+    const int fk = h->fk[side], ck = h->ck[side];
+    const int rlo = h->lo1, rhi = h->hi1;
+    uint32_t *nlive = slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive) + side;
+    int32_t *live = slot_ptr<int32_t>(scratch, L, slot, L.off_live) + side * SPARSE_CAP;
 #pragma unroll
     for (int kk = 0; kk < RC; ++kk) {
         if (!valid[kk]) continue;
         const int j = cb + RC * lane + kk - HALO;
-        const uint32_t *hp = hist + (kk / 2) * 32;
-        const int hs = 16 * (kk & 1);
-        const int base = cb_a[j];                             // items below lo (from the previous level)
-        int cum = base, b1 = -1, b2 = -1, cb1 = 0, cend = 0;
-        for (int b = 0; b < NBIN; ++b) {
-            const int c = (hp[b * HW * 32] >> hs) & 0xffff;
-            if (b1 < 0 && cum + c > fk) { b1 = b; cb1 = cum; }
-            if (b2 < 0 && cum + c > ck) { b2 = b; cend = cum + c; }
-            cum += c;
-        }
-        const int sh = shf[kk], lo = lo_a[j];
-        if (b1 < 0 || b2 < 0) {                               // ranks not inside the binned range
-            atomicOr(&status[k], PAIR_ST_FALLBACK | 4u);      // reason 4: rank outside the binned range
+        const Bracket br = split_bracket<HW * 32>(hist + (kk / 2) * 32, 16 * (kk & 1), 0xffffu, fk, ck, lo_a[j], shf[kk], rlo, rhi);
+        if (br.bad) {                                         // cannot happen: the bins cover every item of the line
+            atomicOr(&status[k], PAIR_ST_FALLBACK | 4u);      // reason 4: rank not found
+            sh_a[j] = -1;
             continue;
         }
-        // new bracket = bins b1..b2; split it again next level unless it is small enough or cannot shrink
-        const int nlo = lo + (b1 << sh);
-        const long long range = (long long)(b2 - b1 + 1) << sh;
-        int sh2 = 0;
-        while ((range >> sh2) > NBIN) ++sh2;
-        // level 1 bins are coarse: split them unless the bracket is already tiny; later levels stop at BRACKET_TARGET
-        const bool done = (cend - cb1 <= (LEVEL == 1 ? 6 : BRACKET_TARGET)) || (sh == 0);
-        lo_a[j] = nlo;
-        w_a[j] = (int)range;
-        cb_a[j] = cb1;
-        sh_a[j] = done ? -1 : sh2;
+        lo_a[j] = br.lo;
+        w_a[j] = br.w;
+        cb_a[j] = br.below;
+        sh_a[j] = br.done ? -1 : br.sh;
+        n_miss += br.miss ? 1 : 0;
+        n_left += br.done ? 0 : 1;
         if (ORIENT == 1) {
             int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
-            rowpack[j] = make_int4(yn[j], nlo - 2 * EPS, (int)range + 4 * EPS, 0);
+            rowpack[j] = make_int4(yn[j], br.lo - 2 * EPS, br.w + 4 * EPS, 0);
+        }
+        if (!br.done) {                                       // the sparse level refines it
+            const unsigned pos = atomicAdd(nlive, 1u);
+            if (pos < SPARSE_CAP) live[pos] = j;
         }
     }
+    n_live = __reduce_add_sync(0xffffffffu, n_live);
+    n_miss = __reduce_add_sync(0xffffffffu, n_miss);
+    n_left = __reduce_add_sync(0xffffffffu, n_left);
+    if (lane == 0) {
+        atomicAdd(&dbg[0], 1u); atomicAdd(&dbg[1], (unsigned)n_live);
+        if (n_miss) atomicAdd(&dbg[2], (unsigned)n_miss);
+        if (n_left) atomicAdd(&dbg[3], (unsigned)n_left);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sparse refinement: the few lines whose bracket is still crowded after the dense level (or whose ranks
+// fell outside the sampled bracket).  One lane owns one line: the 9 owned frames of its window stay in
+// registers, every streamed frame feeds the 9 rows in flight (acc[(a - t) % 9] += e(a, t)), one row
+// completes per step.  The quantised dot products are the same FMA chains as in the sweeps, so the items
+// are identical.  A warp repeats the sweep until all its lines are done (at most SPARSE_LEVELS times).
+// ------------------------------------------------------------------------------------------------
+constexpr int SPARSE_LEVELS = 3;
+
+template <int U>
+__device__ __forceinline__ void sparse_step(const float (&y)[M9][NBINS], int (&acc)[M9], const float4 &x0, const float4 &x1,
+                                            const float4 &x2, float magic) {
+#pragma unroll
+    for (int t = 0; t < M9; ++t) {
+        const float *yt = y[t];
+        float a = __fmaf_rn(x0.x, yt[0], magic);
+        a = __fmaf_rn(x0.y, yt[1], a); a = __fmaf_rn(x0.z, yt[2], a); a = __fmaf_rn(x0.w, yt[3], a);
+        a = __fmaf_rn(x1.x, yt[4], a); a = __fmaf_rn(x1.y, yt[5], a); a = __fmaf_rn(x1.z, yt[6], a);
+        a = __fmaf_rn(x1.w, yt[7], a); a = __fmaf_rn(x2.x, yt[8], a); a = __fmaf_rn(x2.y, yt[9], a);
+        a = __fmaf_rn(x2.z, yt[10], a); a = __fmaf_rn(x2.w, yt[11], a);
+        constexpr int dummy = 0; (void)dummy;
+        const int slot = ((U - t) % M9 + M9) % M9;            // row a - t lives in slot (a - t) % 9
+        if (t == 0) acc[slot] = __float_as_int(a);
+        else acc[slot] += __float_as_int(a);
+    }
+}
+
+__global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+                                                                  int64_t first, int n, FastLayout L,
+                                                                  char *__restrict__ scratch, float magic,
+                                                                  uint32_t *__restrict__ status, uint32_t *__restrict__ dbg) {
+    __shared__ uint32_t s_sp[WPC][NBIN + 2][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int CHUNKS = SPARSE_CAP / 32;
+    const int64_t task = (int64_t)blockIdx.x * WPC + warp;
+    const int slot = (int)(task / (2 * CHUNKS));
+    if (slot >= n) return;
+    const int rem = (int)(task - (int64_t)slot * (2 * CHUNKS));
+    const int side = rem / CHUNKS, chunk = rem - side * CHUNKS;    // side 0: rows (owned = query), 1: columns
+    const uint32_t cnt_all = slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive)[side];
+    const int64_t k = first + slot;
+    if (cnt_all > SPARSE_CAP && chunk == 0 && lane == 0) atomicOr(&status[k], PAIR_ST_FALLBACK | 8u);   // reason 8: too many crowded lines
+    const int cnt = (int)min(cnt_all, (uint32_t)SPARSE_CAP);
+    if (chunk * 32 >= cnt) return;
+    const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
+    const int q = pairs[2 * k];
+    const int nY = side ? h->nr : h->nq, nX = side ? h->nq : h->nr;
+    const float *Qf = ts.frames + ts.offsets[q] * NBINS;
+    const float *Rf = slot_ptr<float>(scratch, L, slot, L.off_rrot);
+    const float *Y = side ? Rf : Qf, *X = side ? Qf : Rf;
+    const int32_t *xn = slot_ptr<int32_t>(scratch, L, slot, side ? L.off_aai : L.off_bbi);
+    const int32_t *yn = slot_ptr<int32_t>(scratch, L, slot, side ? L.off_bbi : L.off_aai);
+    const int line0 = side ? L.max_rows : 0;
+    int32_t *lo_a = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + line0;
+    int32_t *w_a = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + line0;
+    int32_t *cb_a = slot_ptr<int32_t>(scratch, L, slot, L.off_cb) + line0;
+    int32_t *sh_a = slot_ptr<int32_t>(scratch, L, slot, L.off_sh) + line0;
+    const int li = chunk * 32 + lane;
+    bool livel = li < cnt;
+    const int j = livel ? slot_ptr<int32_t>(scratch, L, slot, L.off_live)[side * SPARSE_CAP + li] : 0;
+    // owned window j: frames j .. j+8, pre-doubled (the sweeps double the owned side too)
+    float y[M9][NBINS];
+#pragma unroll
+    for (int t = 0; t < M9; ++t) {
+        const float4 *p = reinterpret_cast<const float4 *>(Y + (int64_t)min(j + t, nY - 1) * NBINS);
+        const float4 v0 = p[0], v1 = p[1], v2 = p[2];
+        y[t][0] = 2.f * v0.x; y[t][1] = 2.f * v0.y; y[t][2] = 2.f * v0.z; y[t][3] = 2.f * v0.w;
+        y[t][4] = 2.f * v1.x; y[t][5] = 2.f * v1.y; y[t][6] = 2.f * v1.z; y[t][7] = 2.f * v1.w;
+        y[t][8] = 2.f * v2.x; y[t][9] = 2.f * v2.y; y[t][10] = 2.f * v2.z; y[t][11] = 2.f * v2.w;
+    }
+    const int ynj = livel ? yn[j] : 0;
+    const int fk = h->fk[side], ck = h->ck[side], rlo = h->lo1, rhi = h->hi1;
+    const int mb9 = M9 * __float_as_int(magic);               // the 9 magic offsets inside a completed sum
+    uint32_t *hist = &s_sp[warp][0][lane];
+    int lo = livel ? lo_a[j] : 0, sh = livel ? sh_a[j] : 0;
+    if (livel && sh < 0) livel = false;
+    const int nrows = nX - 1;                                 // streamed frames 0 .. nX-2
+    int n_swept = 0;
+    for (int lvl = 0; lvl < SPARSE_LEVELS && __any_sync(0xffffffffu, livel); ++lvl) {
+        ++n_swept;
+#pragma unroll 1
+        for (int b = 0; b < NBIN + 2; ++b) hist[b * 32] = 0u;
+        const int yrel = livel ? ynj - lo + (1 << sh) : 0x40000000;   // idle lanes land in the overflow bin
+        const float4 *px = reinterpret_cast<const float4 *>(X);
+        float4 c0 = __ldg(px), c1 = __ldg(px + 1), c2 = __ldg(px + 2);
+        int acc[M9];
+#pragma unroll
+        for (int u = 0; u < M9; ++u) acc[u] = 0;
+        int a = 0;
+        auto step = [&](auto uc) {
+            constexpr int U = decltype(uc)::value;
+            sparse_step<U>(y, acc, c0, c1, c2, magic);
+            px += 3;
+            c0 = __ldg(px); c1 = __ldg(px + 1); c2 = __ldg(px + 2);
+            if (a >= HALO) {                                  // row a - 8 is complete (slot (U + 1) % 9)
+                const int T = acc[(U + 1) % M9] - mb9;
+                const int zr = __ldg(xn + a - HALO) + yrel - T;
+                const int idx = __vimin_s32_relu(zr >> sh, NBIN + 1);
+                atomicAdd(&hist[idx * 32], 1u);
+            }
+            ++a;
+        };
+#pragma unroll 1
+        while (a + M9 <= nrows) {
+            step(IC<0>{}); step(IC<1>{}); step(IC<2>{}); step(IC<3>{}); step(IC<4>{});
+            step(IC<5>{}); step(IC<6>{}); step(IC<7>{}); step(IC<8>{});
+        }
+        const int remr = nrows - a;
+        if (remr > 0) step(IC<0>{});
+        if (remr > 1) step(IC<1>{});
+        if (remr > 2) step(IC<2>{});
+        if (remr > 3) step(IC<3>{});
+        if (remr > 4) step(IC<4>{});
+        if (remr > 5) step(IC<5>{});
+        if (remr > 6) step(IC<6>{});
+        if (remr > 7) step(IC<7>{});
+        __syncwarp();
+        if (livel) {
+            const Bracket br = split_bracket<32>(hist, 0, 0xffffffffu, fk, ck, lo, sh, rlo, rhi);
+            if (br.bad) { atomicOr(&status[k], PAIR_ST_FALLBACK | 4u); livel = false; sh_a[j] = -1; }
+            else {
+                lo = br.lo; sh = br.sh;
+                lo_a[j] = br.lo; w_a[j] = br.w; cb_a[j] = br.below; sh_a[j] = br.done ? -1 : br.sh;
+                if (side == 0) slot_ptr<int4>(scratch, L, slot, L.off_rowpack)[j] = make_int4(ynj, br.lo - 2 * EPS, br.w + 4 * EPS, 0);
+                if (br.done) livel = false;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { atomicAdd(&dbg[0], 1u); atomicAdd(&dbg[1], (unsigned)n_swept); }
+    const unsigned left = __ballot_sync(0xffffffffu, livel);
+    if (lane == 0 && left) atomicAdd(&dbg[2], (unsigned)__popc(left));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -715,7 +1052,7 @@ size_t k2_fast_slot_bytes(const SlotGeom &g, int max_frames) { return make_layou
 
 int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti, int64_t first, int n,
                    const acoss_params &p, const SlotGeom &g, void *scratch, size_t slot_bytes, uint32_t *crp,
-                   float *thr_q, float *thr_r, uint32_t *status, cudaStream_t st, int64_t *launches) {
+                   float *thr_q, float *thr_r, uint32_t *status, uint32_t *dbg, cudaStream_t st, int64_t *launches) {
     if (n <= 0) return ACOSS_OK;
     constexpr int RC = RCV;
     const FastLayout L = make_layout(g, ts.max_frames);
@@ -731,30 +1068,41 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     CUDA_TRY(cudaGetLastError());
     const int outw = Sweep<RC>::OUTW;
     const int strips_c = (g.max_cols + outw - 1) / outw, strips_r = (g.max_rows + outw - 1) / outw;
-    const size_t smem = (size_t)WPC * (NBIN + 1) * (RC / 2) * 32 * 4;
+    const size_t smem = (size_t)WPC * (NBIN + 2) * (RC / 2) * 32 * 4;
+    const size_t smem_sel = (size_t)(SBIN / 2) * SEL_THREADS * 4;
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fast_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
         attr_done = true;
     }
     const unsigned gc = (unsigned)(((int64_t)n * strips_c + WPC - 1) / WPC), gr = (unsigned)(((int64_t)n * strips_r + WPC - 1) / WPC);
-    // level 1 bins the whole item range, levels 2..4 split the bracket again (64x each); a level returns
-    // immediately for strips whose brackets are already small
-    fast_hist_kernel<RC, 0, 1><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status);
-    for (int lvl = 2; lvl <= 4; ++lvl)
-        fast_hist_kernel<RC, 0, 2><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status);
-    fast_hist_kernel<RC, 1, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status);
-    for (int lvl = 2; lvl <= 4; ++lvl)
-        fast_hist_kernel<RC, 1, 2><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status);
+    const int lines = g.max_rows + g.max_cols;
+    // first brackets from every S-th diagonal (sampler + per-line selection), then up to three histogram
+    // levels per orientation; a level returns immediately for strips whose lines are all done
+    static const bool no_sample = getenv("ACOSS_K2_NO_SAMPLE") != nullptr;   // debugging: start from the whole item range
+    if (!no_sample) {
+        const int nu_max = ((g.max_rows - 1) >> L.slog) + ((g.max_cols - 1) >> L.slog) + 1;
+        const int ngrp = (nu_max + SKD - 1) / SKD, nblk = (g.max_rows + SPOS - 1) / SPOS;
+        const int64_t warps = (int64_t)n * ngrp * nblk;
+        fast_sample_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(ts, pairs, first, n, L, base, ngrp, nblk, magic);
+        CUDA_TRY(cudaGetLastError());
+        fast_select_kernel<<<dim3((lines + SEL_THREADS - 1) / SEL_THREADS, n), SEL_THREADS, smem_sel, st>>>(n, L, base);
+        CUDA_TRY(cudaGetLastError());
+    }
+    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg);
+    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 4);
     CUDA_TRY(cudaGetLastError());
+    {
+        const int64_t warps = (int64_t)n * 2 * (SPARSE_CAP / 32);
+        fast_sparse_kernel<<<(unsigned)((warps + WPC - 1) / WPC), 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, magic, status, dbg + 8);
+        CUDA_TRY(cudaGetLastError());
+    }
     fast_emit_kernel<RC><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
     CUDA_TRY(cudaGetLastError());
     fast_scatter_kernel<<<dim3(strips_c, n), 128, 0, st>>>(n, L, base, first, status);
     CUDA_TRY(cudaGetLastError());
-    const int lines = g.max_rows + g.max_cols;
     fast_resolve_thr_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(ts, pairs, first, n, L, base, p.integer_guard, unit,
                                                                        thr_q, thr_r, status);
     CUDA_TRY(cudaGetLastError());

@@ -164,6 +164,17 @@ class Engine:
         check(self._lib.acoss_stage_ms(self._ctx, ms.ctypes.data))
         return dict(k1_oti=float(ms[0]), k2_crp=float(ms[1]), k3_dp=float(ms[2]))
 
+    def debug_counters(self) -> dict:
+        """Diagnostic counters of the last scoring call (acoss_debug_counters): dense histogram level per
+        orientation (strips, live lines, bracket misses, lines left), sparse refinement (warps, sweeps,
+        lines left), listed uncertain cells, exact candidates."""
+        d = np.zeros(32, dtype=np.int64)
+        check(self._lib.acoss_debug_counters(self._ctx, d.ctypes.data))
+        lv = {"col_dense": tuple(int(x) for x in d[0:4]), "row_dense": tuple(int(x) for x in d[4:8]),
+              "sparse": tuple(int(x) for x in d[8:11])}
+        lv["uncertain_cells"] = int(d[24]); lv["exact_candidates"] = int(d[25])
+        return lv
+
     def last_stats(self) -> dict:
         st = np.zeros(8, dtype=np.int64)
         check(self._lib.acoss_last_stats(self._ctx, st.ctypes.data))

@@ -127,6 +127,13 @@ int acoss_knn_sw(acoss_ctx *ctx, const double *csms, const int64_t *offsets, con
  * fallback, [2] kernel launches, [3] cells (sum of M'*N'), [4] exact re-evaluated candidate cells. */
 int acoss_last_stats(acoss_ctx *ctx, int64_t stats[8]);
 
+/* Diagnostic counters of the last acoss_score_pairs* call (valid after acoss_sync).  Dense histogram
+ * level, columns out[0..3] and rows out[4..7]: strips that swept, live lines on entry, lines whose wanted
+ * ranks fell outside the sampled bracket, lines handed to the sparse refinement.  Sparse refinement
+ * out[8..10]: warps, sweeps, lines still crowded at the end.  out[24] uncertain cells the emit sweep
+ * listed, out[25] candidate cells evaluated exactly. */
+int acoss_debug_counters(acoss_ctx *ctx, int64_t out[32]);
+
 /* Per-stage device timing of the pair pipeline, measured with CUDA events on the context stream:
  * acoss_set_profiling(ctx, 1) resets and enables it; acoss_stage_ms returns the accumulated
  * milliseconds of [0] K1 OTI, [1] K2 CRP construction, [2] K3 alignment DP, [3] reserved. */
