@@ -36,7 +36,7 @@ constexpr int SPARSE_CAP = 512;     // live lines per pair and orientation the s
 constexpr int SBIN = 256;           // bins of the per-line sample histogram (select kernel)
 constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
 constexpr int CAND_CAP = 64;        // candidates per row / column
-constexpr int BRACKET_TARGET = 40;  // a bracket holding more cells than this is split by another histogram level
+constexpr int BRACKET_TARGET = 48;  // a bracket holding more cells than this is split by another histogram level
 constexpr int WPC = 4;              // warps per CTA in the sweep kernels
 constexpr int RCV = 4;              // owned frames per lane (register columns) in the sweep kernels
 
@@ -82,9 +82,9 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.off_candd = take((size_t)L.lines * CAND_CAP * 4);
     L.off_rowpack = take((size_t)g.max_rows * 16);
     L.strips_c = (g.max_cols + (32 * RCV - HALO) - 1) / (32 * RCV - HALO);
-    L.slist_cap = 4096;                                   // uncertain cells one emit strip may record
-    while (L.slist_cap < 3 * g.max_rows) L.slist_cap *= 2;
-    L.off_slist = take((size_t)L.strips_c * L.slist_cap * 12);      // 3 words per uncertain cell
+    L.slist_cap = 8192;                                   // uncertain cells one emit strip may record
+    while (L.slist_cap < 4 * g.max_rows) L.slist_cap *= 2;
+    L.off_slist = take((size_t)L.strips_c * L.slist_cap * 8);       // 2 words per uncertain cell: i | j << 14, item
     L.off_scnt = take((size_t)L.strips_c * 4);
     // diagonal sampling stride: the bracket a line gets from n_s samples holds ~2.35 L / sqrt(n_s) cells, which
     // the 64-bin split must bring under BRACKET_TARGET  =>  n_s >= (0.003 L)^2, S = L / n_s <= 1 / (9e-6 L)
@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(128) fast_sample_kernel(TrackSet ts, const int
 // costs another sweep level, never a wrong result (under / overflow are counted exactly).
 // ------------------------------------------------------------------------------------------------
 constexpr int SEL_THREADS = 128;
+constexpr int MIN_SAMPLES = 24;     // lines with fewer samples start from the whole item range
 
 __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(int n, FastLayout L, char *__restrict__ scratch) {
     extern __shared__ uint32_t s_sel_hist[];                 // [SBIN / 2][SEL_THREADS], two 16-bit counters per word
@@ -317,8 +318,12 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(int n, FastLay
         cum += c1;
     }
     int lo = lo1, hi = hi1;
-    if (b_lo >= 0) lo = lo1 + (b_lo << shs);
-    if (b_hi >= 0) hi = min(hi1, lo1 + ((b_hi + 1) << shs));
+    // short lines have too few samples to steer anything: a 64-bin split of the whole item range already
+    // isolates their order statistics (a bin then holds ~L / 40 cells)
+    if (ns >= MIN_SAMPLES) {
+        if (b_lo >= 0) lo = lo1 + (b_lo << shs);
+        if (b_hi >= 0) hi = min(hi1, lo1 + ((b_hi + 1) << shs));
+    }
     int sh = 0;
     while ((((int64_t)hi - lo) >> sh) > NBIN) ++sh;
     slot_ptr<int32_t>(scratch, L, slot, L.off_lo)[line] = lo;
@@ -452,6 +457,10 @@ __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict
 // bracket is the run of bins holding ranks fk and ck (the under / overflow "bins" reach to the end of the
 // pair's item range, the next level splits them).
 // ------------------------------------------------------------------------------------------------
+// cells a finished bracket may hold: BRACKET_TARGET on long lines, a sixteenth of the line on short ones (every
+// bracket cell is an uncertain cell of the emit sweep, and a short line has few cells to begin with)
+__device__ __forceinline__ int bracket_target(int line_len) { return min(BRACKET_TARGET, max(6, line_len >> 4)); }
+
 struct Bracket {
     int lo, w, below, sh;       // new origin, width, exact count of items below lo, shift of the next level
     bool done, miss, bad;
@@ -459,7 +468,7 @@ struct Bracket {
 
 template <int STRIDE>
 __device__ __forceinline__ Bracket split_bracket(const uint32_t *hp, int hs, uint32_t mask, int fk, int ck, int lo, int sh,
-                                                 int rlo, int rhi) {
+                                                 int rlo, int rhi, int target) {
     int cum = 0, b1 = -2, b2 = -2, cb1 = 0, cend = 0;          // the underflow bin counts every item below the bracket
     for (int b = 0; b < NBIN + 2; ++b) {                      // b - 1 = bin of the bracket; -1 under, NBIN over
         const int c = (int)((hp[b * STRIDE] >> hs) & mask);
@@ -476,7 +485,7 @@ __device__ __forceinline__ Bracket split_bracket(const uint32_t *hp, int hs, uin
     int sh2 = 0;
     while ((range >> sh2) > NBIN) ++sh2;
     // split again unless the bracket is small enough or cannot shrink
-    r.done = !r.miss && ((cend - cb1 <= BRACKET_TARGET) || (sh == 0));
+    r.done = !r.miss && ((cend - cb1 <= target) || (sh == 0));
     r.lo = (int)nlo; r.w = (int)range; r.below = cb1; r.sh = sh2;
     return r;
 }
@@ -494,7 +503,8 @@ template <int RC, int ORIENT>
 __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
-                                                             uint32_t *__restrict__ status, uint32_t *__restrict__ dbg) {
+                                                             uint32_t *__restrict__ status, uint32_t *__restrict__ dbg,
+                                                             int min_live, int final_level) {
     extern __shared__ uint32_t s_hist[];                      // [WPC][NBIN + 2][RC / 2][32], two 16-bit counters per word
     using SW = Sweep<RC>;
     static_assert(RC % 2 == 0, "histogram packing needs an even number of register columns");
@@ -543,6 +553,19 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
     int n_live = 0, n_miss = 0, n_left = 0;                  // diagnostics (acoss_debug_counters)
 #pragma unroll
     for (int kk = 0; kk < RC; ++kk) n_live += valid[kk] ? 1 : 0;
+    const int side = (ORIENT == 0) ? 1 : 0;
+    uint32_t *nlive = slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive) + side;
+    int32_t *live = slot_ptr<int32_t>(scratch, L, slot, L.off_live) + side * SPARSE_CAP;
+    if (__reduce_add_sync(0xffffffffu, n_live) < min_live) {
+        // too few live lines to pay for a dense sweep of the strip: they go to the sparse refinement as they are
+#pragma unroll
+        for (int kk = 0; kk < RC; ++kk) {
+            if (!valid[kk]) continue;
+            const unsigned pos = atomicAdd(nlive, 1u);
+            if (pos < SPARSE_CAP) live[pos] = cb + RC * lane + kk - HALO;
+        }
+        return;
+    }
     SW sw;
     sw.init(Y, nY, cb, lane, magic);
     uint32_t *hist = s_hist + (size_t)warp * (NBIN + 2) * HW * 32 + lane;
@@ -561,16 +584,14 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
     });
     __syncwarp();
     // per-thread scan of its own columns' histograms
-    const int side = (ORIENT == 0) ? 1 : 0;
     const int fk = h->fk[side], ck = h->ck[side];
     const int rlo = h->lo1, rhi = h->hi1;
-    uint32_t *nlive = slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive) + side;
-    int32_t *live = slot_ptr<int32_t>(scratch, L, slot, L.off_live) + side * SPARSE_CAP;
 #pragma unroll
     for (int kk = 0; kk < RC; ++kk) {
         if (!valid[kk]) continue;
         const int j = cb + RC * lane + kk - HALO;
-        const Bracket br = split_bracket<HW * 32>(hist + (kk / 2) * 32, 16 * (kk & 1), 0xffffu, fk, ck, lo_a[j], shf[kk], rlo, rhi);
+        const Bracket br = split_bracket<HW * 32>(hist + (kk / 2) * 32, 16 * (kk & 1), 0xffffu, fk, ck, lo_a[j], shf[kk], rlo, rhi,
+                                                  bracket_target(nX - M9));
         if (br.bad) {                                         // cannot happen: the bins cover every item of the line
             atomicOr(&status[k], PAIR_ST_FALLBACK | 4u);      // reason 4: rank not found
             sh_a[j] = -1;
@@ -586,7 +607,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
             int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
             rowpack[j] = make_int4(yn[j], br.lo - 2 * EPS, br.w + 4 * EPS, 0);
         }
-        if (!br.done) {                                       // the sparse level refines it
+        if (!br.done && final_level) {                        // the sparse level refines it
             const unsigned pos = atomicAdd(nlive, 1u);
             if (pos < SPARSE_CAP) live[pos] = j;
         }
@@ -609,6 +630,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, con
 // are identical.  A warp repeats the sweep until all its lines are done (at most SPARSE_LEVELS times).
 // ------------------------------------------------------------------------------------------------
 constexpr int SPARSE_LEVELS = 3;
+constexpr int DENSE2_MIN_LIVE = 16;  // live lines a strip must hold for the second dense level to sweep it
 
 template <int U>
 __device__ __forceinline__ void sparse_step(const float (&y)[M9][NBINS], int (&acc)[M9], const float4 &x0, const float4 &x1,
@@ -719,7 +741,7 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, c
         if (remr > 7) step(IC<7>{});
         __syncwarp();
         if (livel) {
-            const Bracket br = split_bracket<32>(hist, 0, 0xffffffffu, fk, ck, lo, sh, rlo, rhi);
+            const Bracket br = split_bracket<32>(hist, 0, 0xffffffffu, fk, ck, lo, sh, rlo, rhi, bracket_target(nX - M9));
             if (br.bad) { atomicOr(&status[k], PAIR_ST_FALLBACK | 4u); livel = false; sh_a[j] = -1; }
             else {
                 lo = br.lo; sh = br.sh;
@@ -745,8 +767,7 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
                                                              uint32_t *__restrict__ crp_all, int words,
                                                              int64_t crp_words) {
     using SW = Sweep<RC>;
-    static_assert(RC == 2 || RC == 4, "emit word assembly needs RC bits per lane that never straddle a word");
-    constexpr int NW = (24 + 32 * RC + 31) / 32;              // CRP words one strip row can touch
+    static_assert(RC == 4, "emit word assembly: 4 bits per lane that never straddle a word, groups of <= 8 lanes");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t task = (int64_t)blockIdx.x * WPC + warp;
     const int slot = (int)(task / strips_max), strip = (int)(task % strips_max);
@@ -763,114 +784,118 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
     const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
     const int32_t *lo_c = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + L.max_rows;
     const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
-    uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * L.slist_cap * 3;
-    unsigned nlist = 0u;
+    // list of uncertain cells of this strip: 2 words per cell (i | j << 14, fixed-point item).  Every lane fills
+    // chunks of LCH entries it takes from the strip's pool (one returning atomic per chunk), so an append is a
+    // plain lane-private store: no warp cooperation in the sweep
+    constexpr unsigned LCH = 16;
+    const unsigned lcap = (unsigned)L.slist_cap;
+    uint2 *pool = reinterpret_cast<uint2 *>(slot_ptr<uint32_t>(scratch, L, slot, L.off_slist)) + (size_t)strip * lcap;
+    uint32_t *pool_ctr = slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt) + strip;
+    unsigned lp = 0u, lend = 0u;
     uint32_t *crp = crp_all + (int64_t)slot * crp_words;
 
     SW sw;
     sw.init(Y, nY, cb, lane, magic);
-    int ynv[RC], ycl[RC], cw1[RC];                            // bb_fix[j], bb_fix[j] - (colLo - 2 EPS), colW + 4 EPS - 1
-    int jcol[RC];
+    int ynv[RC], ycl[RC];                                     // bb_fix[j], bb_fix[j] - (colLo - 2 EPS)
+    unsigned cw1[RC];                                         // colW + 4 EPS - 1
 #pragma unroll
     for (int kk = 0; kk < RC; ++kk) {
         const int j = cb + RC * lane + kk - HALO;
         const bool valid = (j >= cb) && (j < My) && (j < cb + SW::OUTW);
-        jcol[kk] = j;
-        ynv[kk] = valid ? yn[j] : 0x20000000;                 // invalid: z huge => never in, never a candidate
+        ynv[kk] = valid ? yn[j] : 0x20000000;                 // invalid: item huge => never in, never uncertain
         ycl[kk] = valid ? yn[j] - (lo_c[j] - 2 * EPS) : 0x20000000;
-        cw1[kk] = valid ? w_c[j] + 4 * EPS - 1 : -1;
+        cw1[kk] = valid ? (unsigned)(w_c[j] + 4 * EPS - 1) : 0u;
     }
     // output placement: strip bit t = RC*lane + kk - HALO <-> CRP column cb + t.  cb is a multiple of 8 and the
     // lane's RC bits start at a multiple of RC, so they never straddle a 32-bit word: every lane contributes
-    // its bits to word lword of the row at a position that is constant over the sweep.
+    // a nibble to word lword of the row at a position that is constant over the sweep.
+    const unsigned ij0 = (unsigned)(cb + RC * lane - HALO) << 14;   // column part of a list entry (+ kk << 14)
     const int gpos = (cb & 31) + RC * lane - HALO;
-    const int lword = gpos >> 5;                              // -1 for halo lanes (they contribute nothing)
+    const int lword = gpos >> 5;                              // -1 for halo lanes (their columns are invalid: nibble 0)
     const int lbit = gpos & 31;
-    unsigned bitk[RC];
-#pragma unroll
-    for (int kk = 0; kk < RC; ++kk) bitk[kk] = (lword >= 0) ? (1u << (lbit + kk)) : 0u;
-    const unsigned full = __activemask();                     // all 32 lanes (kept in a register)
-    // lanes that feed the same CRP word form a group; the lowest lane of each group owns the store
+    const unsigned full = 0xffffffffu;
+    // lanes that feed the same CRP word form a group of consecutive lanes; a 3-step segmented OR (shuffle down,
+    // masked by group membership) leaves the complete word in the lowest lane of each group, which owns the store
     const unsigned gmask = __match_any_sync(full, lword);
     const bool gleader = (lword >= 0) && ((gmask & ((1u << lane) - 1u)) == 0u);
+    const unsigned m1 = (lane + 1 < 32 && ((gmask >> (lane + 1)) & 1u)) ? 0xffffffffu : 0u;
+    const unsigned m2 = (lane + 2 < 32 && ((gmask >> (lane + 2)) & 1u)) ? 0xffffffffu : 0u;
+    const unsigned m4 = (lane + 4 < 32 && ((gmask >> (lane + 4)) & 1u)) ? 0xffffffffu : 0u;
     uint32_t *rowp = crp + (cb >> 5) + (lword >= 0 ? lword : 0);    // advances by `words` per row
-    const unsigned ltmask = (1u << lane) - 1u;
-    unsigned ij[RC];                                          // column part of a candidate entry
-#pragma unroll
-    for (int kk = 0; kk < RC; ++kk) ij[kk] = (unsigned)jcol[kk] << 14;
     const int nrows = nX - 1;
-    // Per cell, with z the fixed-point item (sign-bit arithmetic, no predicates):
-    //   ar = z - (rowLo - 2 EPS), ac = z - (colLo - 2 EPS), zp = z - 2 EPS
-    //   certainly in  <=> ar < 0 and ac < 0 and zp >= 0                      sign(ar & ac & ~zp)
-    //   row zone      <=> 0 <= ar <= rw1 (rw1 = rowW + 4 EPS - 1)            !sign(ar | (rw1 - ar))
-    //   uncertain     <=> row zone or column zone or zp < 0 (near-zero item, so F7's NaN is caught exactly)
+    // Per cell, with z the fixed-point item (sign-bit / unsigned-compare arithmetic):
+    //   ar = z - (rowLo - 2 EPS), ac = z - (colLo - 2 EPS)
+    //   certainly in  <=> ar < 0 and ac < 0                                  sign(ar & ac)
+    //   row zone      <=> 0 <= ar <= rw1 (rw1 = rowW + 4 EPS - 1)            (unsigned)ar <= rw1
+    //   near zero     <=> z < 2 EPS  <=>  ar < 4 EPS - rowLo                 (always evaluated exactly: F7's NaN)
+    //   uncertain     <=> row zone or column zone or near zero
+    // A near-zero cell that is certainly in is emitted as 1 and listed as well: its exact evaluation either
+    // confirms a tiny distance (<= both thresholds, resolve checks thr against the zone) or raises the NaN error.
     run_sweep<RC, int4>(sw, X, rowpack, nrows, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
-        const int xr = rp.x - rp.y, xp = rp.x - 2 * EPS, rw1 = rp.z - 1;
-        int ar[RC], ac[RC], ns[RC];
-        unsigned v = 0u;
-        int nsall = -1;
+        const int xr = rp.x - rp.y, nz = 2 * EPS - rp.y;
+        const unsigned rw1 = (unsigned)(rp.z - 1);
+        int ar[RC];
+        bool unc[RC];
+        unsigned nib = 0u;
 #pragma unroll
-        for (int kk = 0; kk < RC; ++kk) {
+        for (int kk = RC - 1; kk >= 0; --kk) {
             ar[kk] = xr + ynv[kk] - sw.T[kk];
-            ac[kk] = rp.x + ycl[kk] - sw.T[kk];
-            const int zp = xp + ynv[kk] - sw.T[kk];
-            const int zr = ar[kk] | (rw1 - ar[kk]), zc = ac[kk] | (cw1[kk] - ac[kk]);
-            ns[kk] = zr & zc & ~zp;                            // sign set <=> NOT uncertain
-            nsall &= ns[kk];
-            v |= (unsigned)((ar[kk] & ac[kk] & ~zp) >> 31) & bitk[kk];
+            const int ac = rp.x + ycl[kk] - sw.T[kk];
+            unc[kk] = ((unsigned)ar[kk] <= rw1) || ((unsigned)ac <= cw1[kk]) || (ar[kk] < nz);
+            nib = __funnelshift_l((unsigned)(ar[kk] & ac), nib, 1);   // sign bit -> bit 0, earlier cells move up
         }
-        // one full-warp REDUX.OR per CRP word the strip row can touch (a partitioned REDUX is slower)
-        unsigned wv = 0u;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const unsigned ww = __reduce_or_sync(full, lword == w ? v : 0u);
-            wv = (lword == w) ? ww : wv;
-        }
-        if (gleader && wv) atomicOr(rowp, wv);
+        unsigned v = nib << lbit;
+        v |= __shfl_down_sync(full, v, 1) & m1;
+        v |= __shfl_down_sync(full, v, 2) & m2;
+        v |= __shfl_down_sync(full, v, 4) & m4;
+        if (gleader && v) atomicOr(rowp, v);
         rowp += words;
-        if (__any_sync(full, nsall >= 0)) {
-            // uncertain cells: raw (i | j << 14, ar, ac) triples appended to the strip-private list with
-            // warp-aggregated positions; fast_scatter_kernel classifies them
+        if (__any_sync(full, (unc[0] || unc[1]) || (unc[2] || unc[3]))) {
+            // uncertain cells go to the lane's own list (no warp cooperation); fast_scatter_kernel classifies them
             const unsigned i = (unsigned)(a - HALO);          // query window (CRP row); i < Mx by construction
 #pragma unroll
             for (int kk = 0; kk < RC; ++kk) {
-                const bool c = ns[kk] >= 0;
-                const unsigned m = __ballot_sync(full, c);
-                const unsigned pos = nlist + __popc(m & ltmask);
-                if (c && pos < (unsigned)L.slist_cap) {
-                    uint32_t *e = slist + (size_t)pos * 3;
-                    e[0] = i | ij[kk]; e[1] = (uint32_t)ar[kk]; e[2] = (uint32_t)ac[kk];
+                if (unc[kk]) {
+                    if (lp == lend) { lp = atomicAdd(pool_ctr, LCH); lend = lp + LCH; }
+                    if (lp < lcap) pool[lp] = make_uint2(i | (ij0 + ((unsigned)kk << 14)), (unsigned)(ar[kk] + rp.y));
+                    ++lp;
                 }
-                nlist += __popc(m);
             }
         }
     });
     (void)Mx;
-    if (lane == 0) slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[strip] = nlist;
+    for (; lp < lend; ++lp)                                   // unused tail of the lane's last chunk
+        if (lp < lcap) pool[lp] = make_uint2(0xffffffffu, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
-// scatter: strip lists -> per-row / per-column candidate lists (the returning atomics live here, in a
+// scatter: lane lists -> per-row / per-column candidate lists (the returning atomics live here, in a
 // kernel with enough parallelism to hide them)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) fast_scatter_kernel(int n, FastLayout L, char *__restrict__ scratch,
-                                                           int64_t first, uint32_t *__restrict__ status) {
+                                                           int64_t first, uint32_t *__restrict__ status,
+                                                           uint32_t *__restrict__ dbg) {
     const int slot = blockIdx.y, strip = blockIdx.x;
     if (slot >= n) return;
     const uint32_t cntv = slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[strip];
     if (cntv > (uint32_t)L.slist_cap && threadIdx.x == 0) atomicOr(&status[first + slot], PAIR_ST_FALLBACK | 16u);   // reason 16: strip list overflow
     const uint32_t m = min(cntv, (uint32_t)L.slist_cap);
-    const uint32_t *slist = slot_ptr<uint32_t>(scratch, L, slot, L.off_slist) + (size_t)strip * L.slist_cap * 3;
+    const uint2 *slist = reinterpret_cast<const uint2 *>(slot_ptr<uint32_t>(scratch, L, slot, L.off_slist)) +
+                         (size_t)strip * L.slist_cap;
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
     const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
+    const int32_t *lo_c = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + L.max_rows;
     const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
+    unsigned total = 0u;
     for (uint32_t e = threadIdx.x; e < m; e += blockDim.x) {
-        const uint32_t v = slist[e * 3];
-        const int ar = (int)slist[e * 3 + 1], ac = (int)slist[e * 3 + 2];   // z - (rowLo - 2 EPS), z - (colLo - 2 EPS)
-        const int i = v & 0x3fff, j = (v >> 14) & 0x3fff;
+        const uint2 rec = slist[e];
+        if (rec.x == 0xffffffffu) continue;                   // unused tail of a lane's chunk
+        ++total;
+        const int i = rec.x & 0x3fff, j = (rec.x >> 14) & 0x3fff;
+        const int z = (int)rec.y;
         const int4 rp = rowpack[i];                           // {aa_fix, rowLo - 2 EPS, rowW + 4 EPS, -}
-        const int z = ar + rp.y;
+        const int ar = z - rp.y, ac = z - (lo_c[j] - 2 * EPS);
         const bool zz = z < 2 * EPS;                          // near-zero item: always evaluated exactly
         const bool rz = (ar >= 0 && ar < rp.z) || zz;
         const bool cz = ac >= 0 && ac < w_c[j] + 4 * EPS;
@@ -884,6 +909,9 @@ __global__ void __launch_bounds__(128) fast_scatter_kernel(int n, FastLayout L, 
             if (p < CAND_CAP) cand[(size_t)line * CAND_CAP + p] = (uint16_t)(i | (ac < 2 * EPS ? 0x8000 : 0));
         }
     }
+    total = __reduce_add_sync(0xffffffffu, total);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && total) atomicAdd(&dbg[24], total);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1091,8 +1119,13 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
         fast_select_kernel<<<dim3((lines + SEL_THREADS - 1) / SEL_THREADS, n), SEL_THREADS, smem_sel, st>>>(n, L, base);
         CUDA_TRY(cudaGetLastError());
     }
-    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg);
-    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 4);
+    // two dense levels per orientation: the second sweeps only strips that still hold DENSE2_MIN_LIVE or more live
+    // lines (short lines start from the whole item range and need it; ordinary strips skip it at once) and hands
+    // every line still live to the sparse refinement
+    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg, 1, 0);
+    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 4, 1, 0);
+    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1);
+    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1);
     CUDA_TRY(cudaGetLastError());
     {
         const int64_t warps = (int64_t)n * 2 * (SPARSE_CAP / 32);
@@ -1101,7 +1134,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     }
     fast_emit_kernel<RC><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
     CUDA_TRY(cudaGetLastError());
-    fast_scatter_kernel<<<dim3(strips_c, n), 128, 0, st>>>(n, L, base, first, status);
+    fast_scatter_kernel<<<dim3(strips_c, n), 128, 0, st>>>(n, L, base, first, status, dbg);
     CUDA_TRY(cudaGetLastError());
     fast_resolve_thr_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(ts, pairs, first, n, L, base, p.integer_guard, unit,
                                                                        thr_q, thr_r, status);
@@ -1109,7 +1142,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     fast_resolve_bits_kernel<<<dim3((lines * 16 + 255) / 256, n), 256, 0, st>>>(n, L, base, thr_q, thr_r, crp, g.words,
                                                                                       g.crp_words);
     CUDA_TRY(cudaGetLastError());
-    if (launches) *launches += 14;
+    if (launches) *launches += 16;
     return ACOSS_OK;
 }
 

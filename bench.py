@@ -233,6 +233,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     stage = eng.stage_ms()
+    k2_debug = eng.debug_counters()                            # of the last timed step
     eng.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local)
     if world > 1:
@@ -316,7 +317,7 @@ def main():
                         "api": "acoss_b200.serra09.Serra09.similarity(idxs) -> host score matrix"},
                 "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "roofline_alu": roofline_alu, "cpu_baseline": cpu,
-                "fallback_pairs": eng.last_stats()["fallback_pairs"]}
+                "fallback_pairs": eng.last_stats()["fallback_pairs"], "k2_debug": k2_debug}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

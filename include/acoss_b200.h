@@ -130,7 +130,8 @@ int acoss_last_stats(acoss_ctx *ctx, int64_t stats[8]);
 /* Diagnostic counters of the last acoss_score_pairs* call (valid after acoss_sync).  Dense histogram
  * level, columns out[0..3] and rows out[4..7]: strips that swept, live lines on entry, lines whose wanted
  * ranks fell outside the sampled bracket, lines handed to the sparse refinement.  Sparse refinement
- * out[8..10]: warps, sweeps, lines still crowded at the end.  out[24] uncertain cells the emit sweep
+ * out[8..10]: warps, sweeps, lines still crowded at the end.  out[12..15] / out[16..19]: the same four
+ * counters for the second (gated) dense level, columns / rows.  out[24] uncertain cells the emit sweep
  * listed, out[25] candidate cells evaluated exactly. */
 int acoss_debug_counters(acoss_ctx *ctx, int64_t out[32]);
 

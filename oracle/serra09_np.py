@@ -29,7 +29,7 @@ F32 = np.float32
 __all__ = [
     "global_chroma", "oti_index", "rotate_reference", "stack_frames",
     "dot_rows_f32_f64", "pairwise_distance", "percentile", "thresholds",
-    "binarize", "chroma_cross_similarity", "qmax", "dmax", "serra09_pair",
+    "binarize", "chroma_cross_similarity", "qmax", "dmax", "dmax_bruteforce", "serra09_pair",
     "kappa_f32", "Serra09Error",
 ]
 
@@ -244,10 +244,21 @@ def qmax(crp: np.ndarray, gamma_o: float = 0.5, gamma_e: float = 0.5, *, return_
     return score
 
 
-def dmax(crp: np.ndarray, gamma_o: float = 0.5, gamma_e: float = 0.5, *, return_matrix=False):
-    """essentia CoverSongSimilarity alignmentType='chen17' (Dmax), 'symmetric' distance.
-    NEXT-row component (``latefusion_chen.py:67-73``): five predecessors
-    (i-1,j-1),(i-2,j-1),(i-1,j-2),(i-3,j-1),(i-1,j-3), i,j >= 3.  UNPINNED restatement."""
+def dmax(crp: np.ndarray, gamma_o: float = 0.5, gamma_e: float = 0.5, *, bonus: bool = True,
+         return_matrix=False):
+    """essentia CoverSongSimilarity alignmentType='chen17' (Dmax, Chen et al. 2017), 'symmetric'
+    distance: the second score ChenFusion stores per pair (``latefusion_chen.py:69-73``).
+    UNPINNED restatement (essentia is absent).  For i, j >= 3:
+
+        P1 = D[i-1][j-1]
+        P2 = D[i-2][j-1] + c[i-1][j]                     P3 = D[i-1][j-2] + c[i][j-1]
+        P4 = D[i-3][j-1] + c[i-2][j] + c[i-1][j]         P5 = D[i-1][j-3] + c[i][j-2] + c[i][j-1]
+        D[i][j] = max(P1..P5) + 1                                         if c[i][j] == 1
+                = max(0, Pk - gamma(c at the predecessor cell of Pk))     otherwise
+
+    **F10** ``bonus``: the ``+ c[..]`` terms of P2..P5 (Chen's bridging of one / two skipped cells)
+    are how upstream essentia is recollected; ``bonus=False`` drops them (plain five-predecessor
+    form).  float32 arithmetic, operations left to right as written."""
     c = np.asarray(crp)
     if not np.isin(c, (0, 1)).all():
         raise Serra09Error("Non-binary elements found in input")
@@ -255,21 +266,47 @@ def dmax(crp: np.ndarray, gamma_o: float = 0.5, gamma_e: float = 0.5, *, return_
     M, N = c.shape
     Q = np.zeros((M, N), dtype=F32)
     go, ge = F32(gamma_o), F32(gamma_e)
-    preds = ((1, 1), (2, 1), (1, 2), (3, 1), (1, 3))
+    cf = c.astype(F32)
     for i in range(3, M):
-        vals, pens = [], []
-        for di, dj in preds:
-            p = Q[i - di, 3 - dj:N - dj]
-            b = c[i - di, 3 - dj:N - dj]
-            vals.append(p)
-            pens.append(p - np.where(b, go, ge))
-        hit = np.maximum.reduce(vals) + F32(1)
-        miss = np.maximum(np.maximum.reduce(pens), F32(0))
-        Q[i, 3:] = np.where(c[i, 3:], hit, miss).astype(F32)
+        sl = lambda r, dj: (r, slice(3 - dj, N - dj))          # cells (r, j - dj) for j = 3..N-1
+        P = [Q[sl(i - 1, 1)].copy(), Q[sl(i - 2, 1)].copy(), Q[sl(i - 1, 2)].copy(),
+             Q[sl(i - 3, 1)].copy(), Q[sl(i - 1, 3)].copy()]
+        if bonus:
+            P[1] = (P[1] + cf[sl(i - 1, 0)]).astype(F32)
+            P[2] = (P[2] + cf[sl(i, 1)]).astype(F32)
+            P[3] = ((P[3] + cf[sl(i - 2, 0)]).astype(F32) + cf[sl(i - 1, 0)]).astype(F32)
+            P[4] = ((P[4] + cf[sl(i, 2)]).astype(F32) + cf[sl(i, 1)]).astype(F32)
+        B = [c[sl(i - 1, 1)], c[sl(i - 2, 1)], c[sl(i - 1, 2)], c[sl(i - 3, 1)], c[sl(i - 1, 3)]]
+        hit = (np.maximum.reduce(P) + F32(1)).astype(F32)
+        pens = [(p - np.where(b, go, ge)).astype(F32) for p, b in zip(P, B)]
+        miss = np.maximum(np.maximum.reduce(pens), F32(0)).astype(F32)
+        Q[i, 3:] = np.where(c[i, 3:], hit, miss)
     score = F32(Q.max()) if Q.size else F32(0)
     if return_matrix:
         return score, Q
     return score
+
+
+def dmax_bruteforce(crp: np.ndarray, gamma_o: float = 0.5, gamma_e: float = 0.5, *, bonus: bool = True):
+    """Cell-by-cell definition of :func:`dmax` (pure Python, small inputs only)."""
+    c = np.asarray(crp).astype(np.int64)
+    M, N = c.shape
+    D = np.zeros((M, N), dtype=F32)
+    g = lambda v: F32(gamma_o) if v else F32(gamma_e)
+    for i in range(3, M):
+        for j in range(3, N):
+            k = F32(1) if bonus else F32(0)
+            P = [D[i - 1, j - 1],
+                 F32(D[i - 2, j - 1] + k * F32(c[i - 1, j])),
+                 F32(D[i - 1, j - 2] + k * F32(c[i, j - 1])),
+                 F32(F32(D[i - 3, j - 1] + k * F32(c[i - 2, j])) + k * F32(c[i - 1, j])),
+                 F32(F32(D[i - 1, j - 3] + k * F32(c[i, j - 2])) + k * F32(c[i, j - 1]))]
+            if c[i, j] == 1:
+                D[i, j] = F32(max(P) + F32(1))
+            else:
+                G = [g(c[i - 1, j - 1]), g(c[i - 2, j - 1]), g(c[i - 1, j - 2]), g(c[i - 3, j - 1]), g(c[i - 1, j - 3])]
+                D[i, j] = max([F32(0)] + [F32(p - q) for p, q in zip(P, G)])
+    return F32(D.max()) if D.size else F32(0)
 
 
 def serra09_pair(query, reference, *, m=9, tau=1, kappa=0.095, oti=True, gamma_o=0.5, gamma_e=0.5,

@@ -13,8 +13,11 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 template <int MODE>
 __global__ void __launch_bounds__(512) bench(float *out, unsigned *gbuf, long long *cyc, int zero) {
     __shared__ unsigned sm[512 * 12];
-    float f[8]; unsigned u[8]; unsigned long long p[8];
+    float f[8]; unsigned u[8]; unsigned long long p[8]; double dd[8];
+    const double da = 1.0 + zero;
     const int tid = threadIdx.x, lane = tid & 31;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dd[i] = threadIdx.x + i;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { f[i] = tid * 0.001f + i; u[i] = tid * 7 + i + zero; p[i] = ((unsigned long long)__float_as_uint(f[i]) << 32) | __float_as_uint(f[i] + 1.f); }
     for (int i = tid; i < 512 * 12; i += 512) sm[i] = i;
@@ -85,6 +88,21 @@ __global__ void __launch_bounds__(512) bench(float *out, unsigned *gbuf, long lo
         } else if (MODE == 16) { // LDS.32 x4 + SHFL x4
 #pragma unroll
             for (int i = 0; i < 4; ++i) { u[i] = sm[(u[i] & 7) * 512 + tid]; u[i + 4] = __shfl_up_sync(0xffffffffu, u[i + 4], 1); }
+        } else if (MODE == 18) { // F2F.F64.F32 x8 (result folded back through the integer bits)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const double d = (double)f[i]; f[i] = __int_as_float(__double2hiint(d) ^ __double2loint(d)); }
+        } else if (MODE == 19) { // DADD x8
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dd[i] = __dadd_rn(dd[i], da);
+        } else if (MODE == 20) { // FMUL + F2F + DADD x8: the exact-item inner step (essentia dotProduct arithmetic)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dd[i] = __dadd_rn(dd[i], (double)__fmul_rn(f[i], a));
+        } else if (MODE == 21) { // FMUL + integer widening (3 ALU) + DADD x8
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned bts = __float_as_uint(__fmul_rn(f[i], a));
+                dd[i] = __dadd_rn(dd[i], __hiloint2double((int)((bts >> 3) + 0x38000000u), (int)(bts << 29)));
+            }
         } else if (MODE == 17) { // byte store to global: 32 contiguous bytes per warp
 #pragma unroll
             for (int i = 0; i < 8; ++i) reinterpret_cast<unsigned char *>(gbuf)[(size_t)(blockIdx.x * 16 + (tid >> 5)) * 65536 + ((it * 8 + i) & 2047) * 32 + lane] = (unsigned char)u[i];
@@ -93,7 +111,7 @@ __global__ void __launch_bounds__(512) bench(float *out, unsigned *gbuf, long lo
     long long t1 = clock64();
     float s = 0; unsigned us = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s += f[i]; us += u[i] + (unsigned)p[i] + (unsigned)(p[i] >> 32); }
+    for (int i = 0; i < 8; ++i) { s += f[i] + (float)dd[i]; us += u[i] + (unsigned)p[i] + (unsigned)(p[i] >> 32); }
     out[blockIdx.x * 512 + tid] = s + us + sm[tid];
     if (tid == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -133,5 +151,9 @@ int main() {
     run<15>("FFMA2 x6 + FADD + ALU x10", 17, out, gbuf, cyc);
     run<16>("LDS.32 x4 + SHFL x4", 8, out, gbuf, cyc);
     run<17>("STG.U8 32B/warp x8", 8, out, gbuf, cyc);
+    run<18>("F2F.F64.F32 x8 (+2 ALU)", 8, out, gbuf, cyc);
+    run<19>("DADD x8", 8, out, gbuf, cyc);
+    run<20>("FMUL + F2F + DADD x8", 8, out, gbuf, cyc);
+    run<21>("FMUL + 3 ALU widen + DADD x8", 8, out, gbuf, cyc);
     return 0;
 }
