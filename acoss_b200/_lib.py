@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libacoss_b200.so")
 
 OK, E_INVALID, E_CUDA, E_TOO_SHORT, E_NAN, E_NONBINARY, E_NOMEM = 0, -1, -2, -3, -4, -5, -6
-ALIGN_QMAX, ALIGN_SW, ALIGN_DMAX = 0, 1, 2
+ALIGN_QMAX, ALIGN_SW, ALIGN_DMAX, ALIGN_DMAX_PLAIN = 0, 1, 2, 3
 CRP_AUTO, CRP_EXACT = 0, 1
 
 
@@ -46,6 +46,7 @@ SIGNATURES = {
     "acoss_set_tracks": (C.c_int, [_vp, _fp, _i64p, C.c_int32, C.c_int]),
     "acoss_score_pairs": (C.c_int, [_vp, _i32p, C.c_int64, C.POINTER(Params), _fp]),
     "acoss_score_pairs_device": (C.c_int, [_vp, _i32p, C.c_int64, C.POINTER(Params), _fp]),
+    "acoss_score_pairs_chen": (C.c_int, [_vp, _i32p, C.c_int64, C.POINTER(Params), _fp, _fp]),
     "acoss_sync": (C.c_int, [_vp]),
     "acoss_stream": (C.c_void_p, [_vp]),
     "acoss_oti_pairs": (C.c_int, [_vp, _i32p, C.c_int64, C.c_int32, _i32p]),

@@ -242,7 +242,10 @@ static int check_params(const acoss_ctx *c, const acoss_params *p) {
     if (p->m < 1 || p->m > 64 || p->tau < 1 || p->tau > 64) { acoss_set_error("m and tau must be in 1..64"); return ACOSS_E_INVALID; }
     if (!(p->kappa >= 0.f && p->kappa <= 1.f)) { acoss_set_error("kappa must be in [0,1]"); return ACOSS_E_INVALID; }
     if (p->noti < 0 || p->noti > 64) { acoss_set_error("noti out of range"); return ACOSS_E_INVALID; }
-    if (p->align != ACOSS_ALIGN_QMAX) { acoss_set_error("align mode %d not implemented for the pair pipeline", p->align); return ACOSS_E_INVALID; }
+    if (p->align != ACOSS_ALIGN_QMAX && p->align != ACOSS_ALIGN_DMAX && p->align != ACOSS_ALIGN_DMAX_PLAIN) {
+        acoss_set_error("align mode %d not implemented for the pair pipeline", p->align);
+        return ACOSS_E_INVALID;
+    }
     const int incr = p->m * p->tau;
     if (c->min_frames < incr + 2) {
         acoss_set_error("a track has %d frames; essentia needs at least m*tau+2 = %d (F9)", c->min_frames, incr + 2);
@@ -271,8 +274,9 @@ struct DumpOut {
 };
 
 // Core pipeline.  pairs_dev / scores_dev are device pointers.
+// scores2_dev (optional): Dmax scores of the same CRPs (ChenFusion), scores_dev then holds Qmax.
 static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const acoss_params *p, float *scores_dev,
-                     DumpOut *dump) {
+                     DumpOut *dump, float *scores2_dev = nullptr) {
     TRY(check_params(c, p));
     if (K <= 0) return ACOSS_OK;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -359,8 +363,12 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
         t2.stop();
         StageTimer t3(c, 2);
         TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p,
-                           (const int32_t *)c->cols.p, n, g.max_cols, p->align, p->gamma_o, p->gamma_e,
-                           scores_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
+                           (const int32_t *)c->cols.p, n, g.max_cols, scores2_dev ? ACOSS_ALIGN_QMAX : p->align,
+                           p->gamma_o, p->gamma_e, scores_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
+        if (scores2_dev)
+            TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p,
+                               (const int32_t *)c->cols.p, n, g.max_cols, ACOSS_ALIGN_DMAX, p->gamma_o, p->gamma_e,
+                               scores2_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
         t3.stop();
         if (dump && first == 0) {
             // single-pair debug dump (K == 1)
@@ -429,6 +437,24 @@ int acoss_score_pairs(acoss_ctx *c, const int32_t *pairs, int64_t K, const acoss
     return acoss_sync(c);
 }
 
+int acoss_score_pairs_chen(acoss_ctx *c, const int32_t *pairs, int64_t K, const acoss_params *p, float *qmax_scores,
+                           float *dmax_scores) {
+    if (!c || (K > 0 && (!pairs || !qmax_scores || !dmax_scores))) { acoss_set_error("score_pairs_chen: NULL argument"); return ACOSS_E_INVALID; }
+    if (K <= 0) return check_params(c, p);
+    for (int64_t k = 0; k < 2 * K; ++k)
+        if (pairs[k] < 0 || pairs[k] >= c->n_tracks) { acoss_set_error("pair index %d out of range", pairs[k]); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(ensure(c->pairs, (size_t)K * 8));
+    TRY(ensure(c->scores, (size_t)K * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->pairs.p, pairs, (size_t)K * 8, cudaMemcpyHostToDevice, c->stream));
+    acoss_params pp = *p;
+    pp.align = ACOSS_ALIGN_QMAX;
+    TRY(run_pairs(c, (const int32_t *)c->pairs.p, K, &pp, (float *)c->scores.p, nullptr, (float *)c->scores.p + K));
+    CUDA_TRY(cudaMemcpyAsync(qmax_scores, c->scores.p, (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dmax_scores, (float *)c->scores.p + K, (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
+    return acoss_sync(c);
+}
+
 int acoss_oti_pairs(acoss_ctx *c, const int32_t *pairs, int64_t K, int32_t noti, int32_t *oti) {
     if (!c || !pairs || !oti || K < 0 || !c->d_frames) { acoss_set_error("oti_pairs: bad arguments"); return ACOSS_E_INVALID; }
     if (K == 0) return ACOSS_OK;
@@ -464,7 +490,10 @@ int acoss_dump_pair(acoss_ctx *c, int32_t q, int32_t r, const acoss_params *p, i
 int acoss_dp_bytes(acoss_ctx *c, const uint8_t *mats, const int64_t *offsets, const int32_t *shapes, int64_t n,
                    int32_t mode, float gamma_o, float gamma_e, float *scores) {
     if (!c || (n > 0 && (!mats || !offsets || !shapes || !scores))) { acoss_set_error("dp_bytes: NULL argument"); return ACOSS_E_INVALID; }
-    if (mode != ACOSS_ALIGN_QMAX && mode != ACOSS_ALIGN_SW) { acoss_set_error("dp_bytes: mode %d not implemented", mode); return ACOSS_E_INVALID; }
+    if (mode != ACOSS_ALIGN_QMAX && mode != ACOSS_ALIGN_SW && mode != ACOSS_ALIGN_DMAX && mode != ACOSS_ALIGN_DMAX_PLAIN) {
+        acoss_set_error("dp_bytes: mode %d not implemented", mode);
+        return ACOSS_E_INVALID;
+    }
     if (n == 0) return ACOSS_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;

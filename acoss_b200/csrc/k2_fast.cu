@@ -821,7 +821,10 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
     const unsigned m1 = (lane + 1 < 32 && ((gmask >> (lane + 1)) & 1u)) ? 0xffffffffu : 0u;
     const unsigned m2 = (lane + 2 < 32 && ((gmask >> (lane + 2)) & 1u)) ? 0xffffffffu : 0u;
     const unsigned m4 = (lane + 4 < 32 && ((gmask >> (lane + 4)) & 1u)) ? 0xffffffffu : 0u;
-    uint32_t *rowp = crp + (cb >> 5) + (lword >= 0 ? lword : 0);    // advances by `words` per row
+    // advances by `words` per row; two rows behind the sweep (segmented-OR pipeline).  Slot 0's rows -2, -1 would
+    // lie before the CRP buffer, but nothing is stored for them (their words are zero)
+    uint32_t *rowp = crp + (cb >> 5) + (lword >= 0 ? lword : 0) - 2 * (int64_t)words;
+    unsigned p1 = 0u, p2 = 0u;
     const int nrows = nX - 1;
     // Per cell, with z the fixed-point item (sign-bit / unsigned-compare arithmetic):
     //   ar = z - (rowLo - 2 EPS), ac = z - (colLo - 2 EPS)
@@ -844,11 +847,15 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
             unc[kk] = ((unsigned)ar[kk] <= rw1) || ((unsigned)ac <= cw1[kk]) || (ar[kk] < nz);
             nib = __funnelshift_l((unsigned)(ar[kk] & ac), nib, 1);   // sign bit -> bit 0, earlier cells move up
         }
-        unsigned v = nib << lbit;
-        v |= __shfl_down_sync(full, v, 1) & m1;
-        v |= __shfl_down_sync(full, v, 2) & m2;
-        v |= __shfl_down_sync(full, v, 4) & m4;
-        if (gleader && v) atomicOr(rowp, v);
+        // the three steps of the segmented OR run on three consecutive rows (independent shuffles, no chain):
+        // this row enters step 1, row a-1 step 2, row a-2 step 4 and is stored
+        const unsigned v0 = nib << lbit;
+        const unsigned t1 = __shfl_down_sync(full, v0, 1), t2 = __shfl_down_sync(full, p1, 2),
+                       t4 = __shfl_down_sync(full, p2, 4);
+        const unsigned vout = p2 | (t4 & m4);
+        if (gleader && vout) atomicOr(rowp, vout);            // rows -2, -1 of the pipeline are all zero
+        p2 = p1 | (t2 & m2);
+        p1 = v0 | (t1 & m1);
         rowp += words;
         if (__any_sync(full, (unc[0] || unc[1]) || (unc[2] || unc[3]))) {
             // uncertain cells go to the lane's own list (no warp cooperation); fast_scatter_kernel classifies them
@@ -864,6 +871,16 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
         }
     });
     (void)Mx;
+    {   // drain the segmented-OR pipeline: rows Mx-2 and Mx-1
+        const unsigned t2 = __shfl_down_sync(full, p1, 2), t4 = __shfl_down_sync(full, p2, 4);
+        const unsigned vout = p2 | (t4 & m4);
+        if (gleader && vout) atomicOr(rowp, vout);
+        p2 = p1 | (t2 & m2);
+        rowp += words;
+        const unsigned t4b = __shfl_down_sync(full, p2, 4);
+        const unsigned vout2 = p2 | (t4b & m4);
+        if (gleader && vout2) atomicOr(rowp, vout2);
+    }
     for (; lp < lend; ++lp)                                   // unused tail of the lane's last chunk
         if (lp < lcap) pool[lp] = make_uint2(0xffffffffu, 0u);
 }
@@ -917,6 +934,20 @@ __global__ void __launch_bounds__(128) fast_scatter_kernel(int n, FastLayout L, 
 // ------------------------------------------------------------------------------------------------
 // resolve: exact re-evaluation of candidate cells, exact order statistics, thresholds, bit patch
 // ------------------------------------------------------------------------------------------------
+// acc_f32prod with the float -> double widening done on the integer pipe (exact for normal non-negative
+// floats; zero / subnormal products take the conversion instruction).  F2F.F64.F32 issues at 16 lanes/clk/SM
+// (profiles/r1_ubench.md), so exact_item alternates the two forms and both pipes share the load.
+__device__ __forceinline__ double acc_f32prod_alu(double acc, float a, float b) {
+    const float p = __fmul_rn(a, b);
+    const uint32_t bts = __float_as_uint(p);
+    double w;
+    if (bts - 0x00800000u < 0x7f000000u)                      // normal, positive, finite
+        w = __hiloint2double((int)((bts >> 3) + 0x38000000u), (int)(bts << 29));
+    else
+        w = (double)p;
+    return __dadd_rn(acc, w);
+}
+
 __device__ __forceinline__ float exact_item(const float *__restrict__ Q, const float *__restrict__ R, int i, int j,
                                             float aa, float bb) {
     // 9 consecutive frames of each side = 108 floats = 27 float4 (frames are 48 B, bases 16 B aligned)
@@ -926,8 +957,8 @@ __device__ __forceinline__ float exact_item(const float *__restrict__ Q, const f
 #pragma unroll 3
     for (int t = 0; t < M9 * NBINS / 4; ++t) {
         const float4 u = __ldg(a + t), v = b[t];
-        acc = acc_f32prod(acc, u.x, v.x); acc = acc_f32prod(acc, u.y, v.y);
-        acc = acc_f32prod(acc, u.z, v.z); acc = acc_f32prod(acc, u.w, v.w);
+        acc = acc_f32prod(acc, u.x, v.x); acc = acc_f32prod_alu(acc, u.y, v.y);
+        acc = acc_f32prod(acc, u.z, v.z); acc = acc_f32prod_alu(acc, u.w, v.w);
     }
     return __fadd_rn(__fsub_rn(aa, __fmul_rn(2.f, (float)acc)), bb);
 }

@@ -1,7 +1,8 @@
-// K3 — Qmax / constrained Smith-Waterman local-alignment DP over bit-packed binary matrices.
+// K3 — Qmax / Dmax / constrained Smith-Waterman local-alignment DP over bit-packed binary matrices.
 //
 // Replaces (file:line under /root/reference, SURVEY.md App. A6 for the essentia part):
 //   essentia CoverSongSimilarity(alignmentType='serra09', distanceType='symmetric')   rqa_serra09.py:64,67
+//   essentia CoverSongSimilarity(alignmentType='chen17',  distanceType='symmetric')   latefusion_chen.py:69-73
 //   smith_waterman_constrained(B)                      acoss/algorithms/utils/alignment_tools.py:26-46
 //
 // Both recurrences read only rows i-1 and i-2 (predecessors (i-1,j-1), (i-2,j-1), (i-1,j-2)), so a
@@ -263,6 +264,106 @@ __global__ void __launch_bounds__(128) dp_scalar_kernel(const uint32_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dmax (essentia alignmentType='chen17'; ChenFusion's second score, latefusion_chen.py:69-73), float32,
+// any gamma.  Five predecessors (u-1,c-1), (u-2,c-1), (u-1,c-2), (u-3,c-1), (u-1,c-3); with BONUS (F10) the
+// skipped-cell predecessors gain Chen's bridging bits:
+//   P2 += b(u-1,c)   P3 += b(u,c-1)   P4 += b(u-2,c) + b(u-1,c)   P5 += b(u,c-2) + b(u,c-1)
+// No same-row dependency either: the row sweep of the other recurrences applies with three previous rows
+// in registers.  A lane owns CW contiguous columns and keeps, per row, a bit window of columns
+// [c0-3, c0+CW) in one register; five halo values cross lanes per row; strips hand the last three columns
+// of every row to the next strip.  Same operations per cell as the oracle: bit-identical floats.
+// ------------------------------------------------------------------------------------------------
+template <int BONUS>
+__global__ void __launch_bounds__(128) dp_dmax_kernel(const uint32_t *__restrict__ bits_all, int64_t slot_words,
+                                                      int wpr, const int32_t *__restrict__ rows_a,
+                                                      const int32_t *__restrict__ cols_a, int n, float go, float ge,
+                                                      float *__restrict__ scores, float4 *__restrict__ halo_all,
+                                                      int64_t halo_pitch) {
+    constexpr int CW = 8, W = 32 * CW;
+    const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pair >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int R = rows_a[pair], C = cols_a[pair];
+    if (R < 4 || C < 4) {
+        if (lane == 0) scores[pair] = 0.f;
+        return;
+    }
+    const uint32_t *bits = bits_all + (int64_t)pair * slot_words;
+    const int nstrips = (C - 3 + W - 1) / W;
+    float4 *halo0 = halo_all + (int64_t)pair * 2 * halo_pitch;
+    float best = 0.f;
+    for (int s = 0; s < nstrips; ++s) {
+        const int c0 = 3 + s * W + lane * CW;       // CRP column of this lane's first DP column
+        const float4 *halo_in = halo0 + (int64_t)(s & 1) * halo_pitch;
+        float4 *halo_out = halo0 + (int64_t)((s + 1) & 1) * halo_pitch;
+        const bool write_halo = (s + 1 < nstrips);
+        // bit k+3+off of a window = CRP bit (row, c0 + k + off); columns >= C are pad zeros
+        auto window = [&](int u) -> uint32_t {
+            const uint32_t *row = bits + (int64_t)u * wpr;
+            const int cw = c0 - 3, w = cw >> 5;
+            const uint32_t lo = (w < wpr) ? __ldg(row + w) : 0u, hi = (w + 1 < wpr) ? __ldg(row + w + 1) : 0u;
+            return __funnelshift_r(lo, hi, cw & 31);
+        };
+        float D1[CW], D2[CW], D3[CW];               // rows u-1, u-2, u-3
+#pragma unroll
+        for (int k = 0; k < CW; ++k) { D1[k] = 0.f; D2[k] = 0.f; D3[k] = 0.f; }
+        uint32_t W1 = window(2), W2 = window(1), W3 = window(0);
+        // (D[c-3], D[c-2], D[c-1]) left of the strip for rows u-1, u-2, u-3 (lane 0 only); rows < 3 are zero
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 h1 = zero4, h2 = zero4, h3 = zero4;
+        uint32_t Wn = window(3);
+        for (int u = 3; u < R; ++u) {
+            const uint32_t W0 = Wn;
+            if (u + 1 < R) Wn = window(u + 1);      // prefetch the next row's bits
+            float l1a = __shfl_up_sync(0xffffffffu, D1[CW - 1], 1), l1b = __shfl_up_sync(0xffffffffu, D1[CW - 2], 1);
+            float l1c = __shfl_up_sync(0xffffffffu, D1[CW - 3], 1);
+            float l2 = __shfl_up_sync(0xffffffffu, D2[CW - 1], 1), l3 = __shfl_up_sync(0xffffffffu, D3[CW - 1], 1);
+            if (lane == 0) { l1a = h1.z; l1b = h1.y; l1c = h1.x; l2 = h2.z; l3 = h3.z; }
+            float Dn[CW];
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+                const float d1m1 = (k >= 1) ? D1[k - 1] : l1a;
+                const float d1m2 = (k >= 2) ? D1[k - 2] : (k == 1 ? l1a : l1b);
+                const float d1m3 = (k >= 3) ? D1[k - 3] : (k == 2 ? l1a : (k == 1 ? l1b : l1c));
+                const float d2m1 = (k >= 1) ? D2[k - 1] : l2;
+                const float d3m1 = (k >= 1) ? D3[k - 1] : l3;
+                auto bit = [&](uint32_t wv, int off) -> uint32_t { return (wv >> (k + 3 + off)) & 1u; };
+                float P1 = d1m1, P2 = d2m1, P3 = d1m2, P4 = d3m1, P5 = d1m3;
+                if (BONUS) {
+                    P2 = __fadd_rn(P2, (float)bit(W1, 0));
+                    P3 = __fadd_rn(P3, (float)bit(W0, -1));
+                    P4 = __fadd_rn(__fadd_rn(P4, (float)bit(W2, 0)), (float)bit(W1, 0));
+                    P5 = __fadd_rn(__fadd_rn(P5, (float)bit(W0, -2)), (float)bit(W0, -1));
+                }
+                float v;
+                if (bit(W0, 0)) {
+                    v = __fadd_rn(fmaxf(fmaxf(fmaxf(P1, P2), fmaxf(P3, P4)), P5), 1.f);
+                } else {
+                    P1 = __fsub_rn(P1, bit(W1, -1) ? go : ge);
+                    P2 = __fsub_rn(P2, bit(W2, -1) ? go : ge);
+                    P3 = __fsub_rn(P3, bit(W1, -2) ? go : ge);
+                    P4 = __fsub_rn(P4, bit(W3, -1) ? go : ge);
+                    P5 = __fsub_rn(P5, bit(W1, -3) ? go : ge);
+                    v = fmaxf(fmaxf(fmaxf(P1, P2), fmaxf(P3, P4)), fmaxf(P5, 0.f));
+                }
+                Dn[k] = v;
+                if (c0 + k < C) best = fmaxf(best, v);
+            }
+            const float4 hnew = (lane == 0 && s > 0) ? halo_in[u] : zero4;
+            if (write_halo && lane == 31) halo_out[u] = make_float4(Dn[CW - 3], Dn[CW - 2], Dn[CW - 1], 0.f);
+#pragma unroll
+            for (int k = 0; k < CW; ++k) { D3[k] = D2[k]; D2[k] = D1[k]; D1[k] = Dn[k]; }
+            W3 = W2; W2 = W1; W1 = W0;
+            h3 = h2; h2 = h1; h1 = hnew;
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) scores[pair] = best;
+}
+
+// ------------------------------------------------------------------------------------------------
 // helpers: pair geometry, byte-matrix packing
 // ------------------------------------------------------------------------------------------------
 __global__ void pair_geometry_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n, int incr,
@@ -371,6 +472,12 @@ int launch_dp_bits(const uint32_t *bits, int64_t slot_words, int words_per_row, 
     else if (mode == ACOSS_ALIGN_SW)
         dp_scalar_kernel<MODE_SW><<<blocks, 128, 0, st>>>(bits, slot_words, words_per_row, rows, cols, n, gamma_o,
                                                           gamma_e, scores, (float4 *)halo_scratch, halo_pitch);
+    else if (mode == ACOSS_ALIGN_DMAX)
+        dp_dmax_kernel<1><<<blocks, 128, 0, st>>>(bits, slot_words, words_per_row, rows, cols, n, gamma_o, gamma_e,
+                                                  scores, (float4 *)halo_scratch, halo_pitch);
+    else if (mode == ACOSS_ALIGN_DMAX_PLAIN)
+        dp_dmax_kernel<0><<<blocks, 128, 0, st>>>(bits, slot_words, words_per_row, rows, cols, n, gamma_o, gamma_e,
+                                                  scores, (float4 *)halo_scratch, halo_pitch);
     else {
         acoss_set_error("alignment mode %d is not implemented", mode);
         return ACOSS_E_INVALID;

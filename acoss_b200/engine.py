@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import ALIGN_QMAX, ALIGN_SW, AcossError, Params, check, default_params  # noqa: F401
+from ._lib import ALIGN_DMAX, ALIGN_DMAX_PLAIN, ALIGN_QMAX, ALIGN_SW, AcossError, Params, check, default_params  # noqa: F401
 
 __all__ = ["Engine", "AcossError", "default_params", "pack_tracks"]
 
@@ -89,6 +89,16 @@ class Engine:
         check(self._lib.acoss_score_pairs(self._ctx, pairs.ctypes.data, len(pairs), C.byref(params),
                                           out.ctypes.data))
         return out
+
+    def score_pairs_chen(self, pairs, params: Params | None = None):
+        """ChenFusion flavour: (qmax, dmax) float32 arrays of the same CRPs (acoss_score_pairs_chen)."""
+        params = params or default_params()
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        q = np.empty(len(pairs), dtype=np.float32)
+        d = np.empty(len(pairs), dtype=np.float32)
+        check(self._lib.acoss_score_pairs_chen(self._ctx, pairs.ctypes.data, len(pairs), C.byref(params),
+                                               q.ctypes.data, d.ctypes.data))
+        return q, d
 
     def score_pairs_device(self, pairs_ptr: int, n_pairs: int, scores_ptr: int, params: Params | None = None):
         """Device in / device out, asynchronous on the engine stream; call sync()."""

@@ -45,7 +45,8 @@ class Serra09(CoverAlgorithm):
 
     def __init__(self, dataset_csv, datapath, chroma_type='hpcp', shortname='benchmark',
                  oti=True, kappa=0.095, tau=1, m=9, downsample_fac=40, device=0, features=None,
-                 gamma_o=0.5, gamma_e=0.5, tile_pairs=1 << 16, cachedir="cache", engine=None):
+                 gamma_o=0.5, gamma_e=0.5, tile_pairs=1 << 16, cachedir="cache", engine=None,
+                 _name="Serra09", _similarity_types=("main",)):
         self.oti = oti
         self.tau = tau
         self.m = m
@@ -60,8 +61,9 @@ class Serra09(CoverAlgorithm):
         self.all_feats = {}                      # cached (downsampled) chroma per song
         self._engine = engine
         self._resident = False
-        CoverAlgorithm.__init__(self, dataset_csv=dataset_csv, name="Serra09", datapath=datapath,
-                                shortname=shortname, cachedir=cachedir, features=features)
+        CoverAlgorithm.__init__(self, dataset_csv=dataset_csv, name=_name, datapath=datapath,
+                                shortname=shortname, cachedir=cachedir, features=features,
+                                similarity_types=list(_similarity_types))
 
     # ------------------------------------------------------------------------------------------
     def load_features(self, i):

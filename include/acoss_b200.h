@@ -41,6 +41,7 @@ extern "C" {
 #define ACOSS_ALIGN_QMAX 0      /* essentia CoverSongSimilarity alignmentType='serra09'            */
 #define ACOSS_ALIGN_SW 1        /* alignment_tools.py:26-46 smith_waterman_constrained             */
 #define ACOSS_ALIGN_DMAX 2      /* essentia alignmentType='chen17' (latefusion_chen.py:69-71)      */
+#define ACOSS_ALIGN_DMAX_PLAIN 3 /* F10 switch: Dmax without Chen's bridging terms                 */
 
 /* CRP construction path (acoss_params.crp_path) */
 #define ACOSS_CRP_AUTO 0        /* fast sweep kernels, exact per-pair fallback when a check fails  */
@@ -96,6 +97,12 @@ int acoss_score_pairs_device(acoss_ctx *ctx, const int32_t *pairs_dev, int64_t n
 int acoss_sync(acoss_ctx *ctx);
 /* Returns the context's CUDA stream (a cudaStream_t) so callers can record events on it. */
 void *acoss_stream(acoss_ctx *ctx);
+
+/* Replaces ChenFusion.similarity(idxs) (latefusion_chen.py:58-73) for a whole batch: the same CRP per
+ * pair feeds both alignments; qmax_scores[k] / dmax_scores[k] are the floats the reference stores in
+ * Ds["qmax"][i][j] / Ds["dmax"][i][j].  p->align is ignored.  Host buffers. */
+int acoss_score_pairs_chen(acoss_ctx *ctx, const int32_t *pairs, int64_t n_pairs, const acoss_params *p,
+                           float *qmax_scores, float *dmax_scores);
 
 /* K1 only — essentia optimalTranspositionIndex (inside ChromaCrossSimilarity, App. A1). */
 int acoss_oti_pairs(acoss_ctx *ctx, const int32_t *pairs, int64_t n_pairs, int32_t noti, int32_t *oti);

@@ -104,6 +104,48 @@ float oracle_qmax(const uint8_t *c, int M, int N, float go, float ge) {
     return best;
 }
 
+/* Dmax (chen17, symmetric) -- the second score of ChenFusion.similarity (latefusion_chen.py:69-73).
+ * Five predecessors, i, j >= 3; `bonus` (F10) adds Chen's bridging terms c[i-1][j], c[i][j-1], ... to the
+ * skipped-cell predecessors.  float32, operations left to right.  UNPINNED restatement. */
+float oracle_dmax(const uint8_t *c, int M, int N, float go, float ge, int bonus) {
+    if (M <= 0 || N <= 0) return 0.f;
+    float *D = (float *)calloc((size_t)M * N, sizeof(float));
+    float best = 0.f;
+#define CC(i, j) c[(size_t)(i) * N + (j)]
+#define DD(i, j) D[(size_t)(i) * N + (j)]
+    for (int i = 3; i < M; i++) {
+        for (int j = 3; j < N; j++) {
+            float P[5];
+            P[0] = DD(i - 1, j - 1);
+            P[1] = DD(i - 2, j - 1); P[2] = DD(i - 1, j - 2);
+            P[3] = DD(i - 3, j - 1); P[4] = DD(i - 1, j - 3);
+            if (bonus) {
+                P[1] = P[1] + (float)CC(i - 1, j);
+                P[2] = P[2] + (float)CC(i, j - 1);
+                P[3] = (P[3] + (float)CC(i - 2, j)) + (float)CC(i - 1, j);
+                P[4] = (P[4] + (float)CC(i, j - 2)) + (float)CC(i, j - 1);
+            }
+            float v;
+            if (CC(i, j) == 1) {
+                v = fmaxf(fmaxf(fmaxf(P[0], P[1]), fmaxf(P[2], P[3])), P[4]) + 1.f;
+            } else {
+                P[0] -= CC(i - 1, j - 1) ? go : ge;
+                P[1] -= CC(i - 2, j - 1) ? go : ge;
+                P[2] -= CC(i - 1, j - 2) ? go : ge;
+                P[3] -= CC(i - 3, j - 1) ? go : ge;
+                P[4] -= CC(i - 1, j - 3) ? go : ge;
+                v = fmaxf(fmaxf(fmaxf(P[0], P[1]), fmaxf(P[2], P[3])), fmaxf(P[4], 0.f));
+            }
+            DD(i, j) = v;
+            if (v > best) best = v;
+        }
+    }
+#undef CC
+#undef DD
+    free(D);
+    return best;
+}
+
 /* in-tree smith_waterman_constrained (alignment_tools.py:26-46), float64 like the reference */
 double oracle_sw_constrained(const uint8_t *B, int M, int N) {
     double best = 0.0;
@@ -130,9 +172,9 @@ double oracle_sw_constrained(const uint8_t *B, int M, int N) {
 
 /* One pair.  Outputs (any may be NULL): oti, crp (M'*N' bytes), thr_q (M'), thr_r (N'),
  * d (M'*N' floats).  Returns 0 ok, -1 too-short/empty input, -2 NaN distance (F7). */
-int oracle_serra09_pair(const float *q, int nq, const float *r_in, int nr, const oracle_params *p,
-                        float *score, int *oti_out, uint8_t *crp_out, float *thr_q_out,
-                        float *thr_r_out, float *d_out) {
+static int pair_impl(const float *q, int nq, const float *r_in, int nr, const oracle_params *p,
+                     float *score, float *score_dmax, int *oti_out, uint8_t *crp_out, float *thr_q_out,
+                     float *thr_r_out, float *d_out) {
     const int m = p->m, tau = p->tau, dim = m * NB, incr = m * tau;
     if (nq <= 0 || nr <= 0) return -1;
     if (m > 1 && (nq < incr + 1 || nr < incr + 1)) return -1;
@@ -198,15 +240,25 @@ int oracle_serra09_pair(const float *q, int nq, const float *r_in, int nr, const
     if (crp_out) memcpy(crp_out, c, (size_t)M * N);
     int rc = 0;
     if (has_nan) rc = -2;
-    else if (score) *score = oracle_qmax(c, M, N, p->gamma_o, p->gamma_e);
+    else {
+        if (score) *score = oracle_qmax(c, M, N, p->gamma_o, p->gamma_e);
+        if (score_dmax) *score_dmax = oracle_dmax(c, M, N, p->gamma_o, p->gamma_e, 1);
+    }
     free(c); free(tmp); free(thr_r); free(thr_q); free(bbv); free(d); free(rs); free(qs); free(r);
     return rc;
+}
+
+int oracle_serra09_pair(const float *q, int nq, const float *r_in, int nr, const oracle_params *p,
+                        float *score, int *oti_out, uint8_t *crp_out, float *thr_q_out,
+                        float *thr_r_out, float *d_out) {
+    return pair_impl(q, nq, r_in, nr, p, score, NULL, oti_out, crp_out, thr_q_out, thr_r_out, d_out);
 }
 
 /* ---- batched, multi-threaded driver (stands in for joblib.Parallel over pair chunks) ---- */
 typedef struct {
     const float *frames; const int64_t *offsets; const int32_t *pairs; int64_t K;
     const oracle_params *p; float *scores; int *status; int64_t *next; pthread_mutex_t *mu;
+    float *scores_dmax;
 } job_t;
 
 static void *worker(void *arg) {
@@ -218,27 +270,35 @@ static void *worker(void *arg) {
         if (k >= jb->K) break;
         int32_t a = jb->pairs[2 * k], b = jb->pairs[2 * k + 1];
         const float *q = jb->frames + jb->offsets[a] * NB, *r = jb->frames + jb->offsets[b] * NB;
-        float sc = 0.f;
-        int rc = oracle_serra09_pair(q, (int)(jb->offsets[a + 1] - jb->offsets[a]), r,
-                                     (int)(jb->offsets[b + 1] - jb->offsets[b]), jb->p, &sc, NULL, NULL,
-                                     NULL, NULL, NULL);
+        float sc = 0.f, sd = 0.f;
+        int rc = pair_impl(q, (int)(jb->offsets[a + 1] - jb->offsets[a]), r,
+                           (int)(jb->offsets[b + 1] - jb->offsets[b]), jb->p, &sc, jb->scores_dmax ? &sd : NULL,
+                           NULL, NULL, NULL, NULL, NULL);
         jb->scores[k] = sc;
+        if (jb->scores_dmax) jb->scores_dmax[k] = sd;
         if (rc != 0) *jb->status = rc;
     }
     return NULL;
 }
 
-int oracle_serra09_pairs(const float *frames, const int64_t *offsets, const int32_t *pairs, int64_t K,
-                         const oracle_params *p, int nthreads, float *scores) {
+/* ChenFusion.similarity over a batch: qmax and dmax of the same CRP (latefusion_chen.py:58-73);
+ * scores_dmax may be NULL (= Serra09.similarity). */
+int oracle_chen_pairs(const float *frames, const int64_t *offsets, const int32_t *pairs, int64_t K,
+                      const oracle_params *p, int nthreads, float *scores_qmax, float *scores_dmax) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 1024) nthreads = 1024;
     pthread_t th[1024];
     pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
     int64_t next = 0; int status = 0;
-    job_t jb = {frames, offsets, pairs, K, p, scores, &status, &next, &mu};
+    job_t jb = {frames, offsets, pairs, K, p, scores_qmax, &status, &next, &mu, scores_dmax};
     for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, worker, &jb);
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     return status;
+}
+
+int oracle_serra09_pairs(const float *frames, const int64_t *offsets, const int32_t *pairs, int64_t K,
+                         const oracle_params *p, int nthreads, float *scores) {
+    return oracle_chen_pairs(frames, offsets, pairs, K, p, nthreads, scores, NULL);
 }
 
 /* batched Smith-Waterman over byte matrices laid out back to back */

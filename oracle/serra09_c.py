@@ -35,6 +35,11 @@ def lib():
         L.oracle_oti.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int]
         L.oracle_qmax.restype = C.c_float
         L.oracle_qmax.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.oracle_dmax.restype = C.c_float
+        L.oracle_dmax.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
+        L.oracle_chen_pairs.restype = C.c_int
+        L.oracle_chen_pairs.argtypes = [fp, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.POINTER(OracleParams), C.c_int, fp, fp]
         L.oracle_sw_constrained.restype = C.c_double
         L.oracle_sw_constrained.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_serra09_pair.restype = C.c_int
@@ -62,6 +67,11 @@ def oti(q, r, noti=12) -> int:
 def qmax(crp, gamma_o=0.5, gamma_e=0.5) -> float:
     c = np.ascontiguousarray(crp, np.uint8)
     return float(lib().oracle_qmax(c.ctypes.data, c.shape[0], c.shape[1], gamma_o, gamma_e))
+
+
+def dmax(crp, gamma_o=0.5, gamma_e=0.5, bonus=True) -> float:
+    c = np.ascontiguousarray(crp, np.uint8)
+    return float(lib().oracle_dmax(c.ctypes.data, c.shape[0], c.shape[1], gamma_o, gamma_e, int(bonus)))
 
 
 def sw_constrained(B) -> float:
@@ -109,6 +119,20 @@ def pairs(frames, offsets, pair_idx, p: OracleParams | None = None, nthreads=1):
     if rc != 0:
         raise RuntimeError("oracle: pair batch failed rc=%d" % rc)
     return out
+
+
+def chen_pairs(frames, offsets, pair_idx, p: OracleParams | None = None, nthreads=1):
+    """ChenFusion.similarity over a batch: (qmax, dmax) score arrays of the same CRPs."""
+    p = p or params()
+    frames = np.ascontiguousarray(frames, np.float32)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    pair_idx = np.ascontiguousarray(pair_idx, np.int32)
+    q = np.zeros(len(pair_idx), np.float32); d = np.zeros(len(pair_idx), np.float32)
+    rc = lib().oracle_chen_pairs(_fp(frames), offsets.ctypes.data, pair_idx.ctypes.data, len(pair_idx),
+                                 C.byref(p), int(nthreads), _fp(q), _fp(d))
+    if rc != 0:
+        raise RuntimeError("oracle: pair batch failed rc=%d" % rc)
+    return q, d
 
 
 def sw_batch(mats, nthreads=1):

@@ -15,6 +15,7 @@ What is executed (file:line under /root/reference):
                                                       where numba 0.65 cannot type them)
   acoss/algorithms/algorithm_template.py:205-290      CoverAlgorithm.getEvalStatistics
   acoss/algorithms/rqa_serra09.py:71-83               Serra09.normalize_by_length
+  acoss/algorithms/latefusion_chen.py:75-85           ChenFusion.normalize_by_length
 The Serra09 essentia calls themselves cannot be executed (essentia absent): no golden for them.
 """
 import importlib.util
@@ -172,10 +173,23 @@ def evalstats_golden():
         s.normalize_by_length()
         norm = dict(n_frames=n_frames, seed=8, scale=40.0,
                     out=[[float(x) for x in row] for row in s.Ds["main"]])
+        # ChenFusion.normalize_by_length (latefusion_chen.py:75-85): norm_fac / score, zero scores -> inf
+        from acoss.algorithms.latefusion_chen import ChenFusion
+        cf = ChenFusion.__new__(ChenFusion)
+        Dq = np.floor(np.random.default_rng(9).random((9, 9)) * 60).astype(np.float32) * np.float32(0.5)
+        Dd = np.floor(np.random.default_rng(10).random((9, 9)) * 90).astype(np.float32) * np.float32(0.5)
+        np.fill_diagonal(Dq, 0); np.fill_diagonal(Dd, 0)
+        cf.Ds = {"qmax": Dq.copy(), "dmax": Dd.copy()}
+        cf.filepaths = [None] * 9
+        cf.all_feats = {i: np.zeros((n, 12), dtype=np.float32) for i, n in enumerate(n_frames)}
+        with np.errstate(divide="ignore"):
+            cf.normalize_by_length()
+        tolist = lambda M: [[("inf" if np.isinf(x) else float(x)) for x in row] for row in M]
+        norm_chen = dict(n_frames=n_frames, seeds=[9, 10], qmax=tolist(cf.Ds["qmax"]), dmax=tolist(cf.Ds["dmax"]))
     finally:
         os.chdir(cwd)
     with open(os.path.join(HERE, "evalstats_golden.json"), "w") as f:
-        json.dump(dict(eval_cases=cases, normalize=norm), f, indent=1)
+        json.dump(dict(eval_cases=cases, normalize=norm, normalize_chen=norm_chen), f, indent=1)
     print("wrote evalstats_golden.json:", len(cases), "eval cases")
 
 

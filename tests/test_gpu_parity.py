@@ -208,3 +208,40 @@ def test_nonbinary_raises(eng):
     with pytest.raises(AcossError) as ei:
         eng.dp_bytes([np.full((5, 5), 2)], ALIGN_SW)
     assert ei.value.code == E_NONBINARY
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (300, 1030), (130, 600), (70, 2100), (900, 70), (3, 3), (4, 4),
+                                   (4, 50), (50, 4), (5, 33), (259, 259), (260, 261)])
+def test_dmax_shapes(eng, shape):
+    """Dmax (chen17): strip boundaries at 256 columns, multi-strip halos, degenerate sizes, F10 switch,
+    general gammas — float32 results identical to the oracle."""
+    from acoss_b200.engine import ALIGN_DMAX, ALIGN_DMAX_PLAIN
+    from oracle import serra09_c as oc
+    rng = np.random.default_rng(sum(shape) + 1)
+    mats = [(rng.random(shape) < p).astype(np.uint8) for p in (0.05, 0.12, 0.4)]
+    assert list(eng.dp_bytes(mats, ALIGN_DMAX)) == [oc.dmax(m) for m in mats]
+    assert list(eng.dp_bytes(mats, ALIGN_DMAX_PLAIN)) == [oc.dmax(m, bonus=False) for m in mats]
+    assert list(eng.dp_bytes(mats, ALIGN_DMAX, 0.5, 0.7)) == [oc.dmax(m, 0.5, 0.7) for m in mats]
+
+
+def test_dmax_known_answers(eng):
+    from acoss_b200.engine import ALIGN_DMAX
+    got = eng.dp_bytes([np.eye(50, dtype=np.uint8), np.ones((50, 50), np.uint8)], ALIGN_DMAX)
+    assert list(got) == [47.0, 71.0]              # oracle/serra09_np.py::dmax (tests/test_oracle_serra09.py)
+
+
+def test_chen_pairs_both_scores(eng):
+    """acoss_score_pairs_chen: Qmax and Dmax of the same CRPs equal the oracle's, and Qmax equals the
+    Serra09 entry point."""
+    from acoss_b200 import pack_tracks
+    from oracle import serra09_c as oc
+    rng = np.random.default_rng(31)
+    tracks = [hp(rng, n) for n in (120, 333, 280, 64, 410)]
+    tracks.append(np.roll(tracks[1], 4, axis=1))
+    frames, offs = pack_tracks(tracks)
+    eng.set_tracks(frames, offs)
+    pairs = np.array([(i, j) for i in range(len(tracks)) for j in range(i + 1, len(tracks))], np.int32)
+    q, d = eng.score_pairs_chen(pairs)
+    wq, wd = oc.chen_pairs(frames, offs, pairs, nthreads=8)
+    assert np.array_equal(q, wq) and np.array_equal(d, wd)
+    assert np.array_equal(q, eng.score_pairs(pairs))

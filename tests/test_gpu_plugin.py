@@ -121,3 +121,30 @@ def test_earlyfusion_plugin(workdir):
         for k in want:
             assert e.Ds[k][i, j] == pytest.approx(want[k], rel=1e-5)
     e.close()
+
+
+def test_chenfusion_dropin(workdir):
+    """ChenFusion.all_pairwise -> normalize_by_length -> getEvalStatistics per key, against the same
+    sequence fed with the CPU oracle's Qmax / Dmax scores."""
+    from acoss_b200 import pack_tracks, synthetic
+    from acoss_b200.chenfusion import ChenFusion
+    from oracle import evalstats_np as ev
+    from oracle import serra09_c as oc
+    tracks, labels = synthetic.config_dataset("tiny")
+    feats = [dict(hpcp=t, label="w%d" % l) for t, l in zip(tracks, labels)]
+    c = ChenFusion(None, None, features=feats, downsample_fac=1, shortname="tinychen")
+    c.all_pairwise(parallel=0, n_cores=1, symmetric=True)
+    frames, offs = pack_tracks(tracks)
+    pairs = synthetic.all_pairs_upper(len(tracks))
+    wq, wd = oc.chen_pairs(frames, offs, pairs, nthreads=8)
+    for key, w in (("qmax", wq), ("dmax", wd)):
+        D = np.zeros((len(tracks), len(tracks)), np.float32)
+        D[pairs[:, 0], pairs[:, 1]] = w
+        assert np.array_equal(np.array(c.Ds[key]), ev.symmetrize(D))
+    c.normalize_by_length()
+    lens = np.array([len(t) for t in tracks], np.float64)
+    with np.errstate(divide="ignore"):
+        want = (np.sqrt(lens)[None, :] / ev.symmetrize(D).astype(np.float64)).astype(np.float32)
+    assert np.array_equal(np.array(c.Ds["dmax"]), want)
+    c.cleanup_memmap()
+    c.close()

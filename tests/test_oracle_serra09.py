@@ -159,3 +159,34 @@ def test_sw_c_port(golden_dir):
     for (seed, m, n, p), (s, _) in zip(g["sw_meta"][:6], g["sw_scores"][:6]):
         B = (np.random.default_rng(int(seed)).random((int(m), int(n))) < p).astype(np.uint8)
         assert oc.sw_constrained(B) == pytest.approx(s, abs=1e-9)
+
+
+def test_dmax_restatement_self_consistency():
+    """Row-vectorised Dmax == cell-by-cell definition == plain-C port, with and without Chen's bridging
+    terms (F10), default and general gammas; known answers on structured matrices."""
+    from oracle import serra09_c as oc
+    from oracle import serra09_np as o
+    rng = np.random.default_rng(3)
+    for shape, p in [((40, 50), 0.15), ((30, 30), 0.3), ((5, 60), 0.2), ((64, 64), 0.1), ((3, 3), 0.5), ((4, 7), 0.9)]:
+        c = (rng.random(shape) < p).astype(np.uint8)
+        for bonus in (True, False):
+            for g in ((0.5, 0.5), (0.5, 0.7), (0.3, 0.9)):
+                a = float(o.dmax(c, *g, bonus=bonus))
+                assert a == float(o.dmax_bruteforce(c, *g, bonus=bonus)) == oc.dmax(c, *g, bonus=bonus)
+    assert float(o.dmax(np.eye(50, dtype=np.uint8))) == 47.0          # the diagonal alone: M - 3
+    assert float(o.dmax(np.ones((50, 50), np.uint8))) == 71.0        # bridging terms add 3 per 2 rows
+    assert float(o.dmax(np.ones((50, 50), np.uint8), bonus=False)) == 47.0
+    assert float(o.dmax(np.ones((3, 9), np.uint8))) == 0.0           # DP starts at (3, 3)
+    with pytest.raises(o.Serra09Error):
+        o.dmax(np.full((5, 5), 2))
+
+
+def test_chen_pairs_c_matches_numpy():
+    from oracle import serra09_c as oc
+    from oracle import serra09_np as o
+    rng = np.random.default_rng(8)
+    Q, R = hp(rng, 70), hp(rng, 55)
+    frames = np.concatenate([Q, R]); offs = np.array([0, 70, 125], np.int64)
+    q, d = oc.chen_pairs(frames, offs, np.array([[0, 1]], np.int32))
+    crp = o.chroma_cross_similarity(Q, R)
+    assert float(q[0]) == float(o.qmax(crp)) and float(d[0]) == float(o.dmax(crp))

@@ -147,3 +147,28 @@ def test_earlyfusion_host_helpers(golden_dir):
     assert list(sig.parameters)[1:13] == ["dataset_csv", "datapath", "chroma_type", "shortname", "blocksize",
                                           "mfccs_per_block", "ssm_res", "chromas_per_block", "kappa", "K",
                                           "niters", "log_times"]
+
+
+def test_chenfusion_signature_and_normalize(workdir):
+    """ChenFusion mirror (latefusion_chen.py:18-91): constructor signature, score keys, algorithm name,
+    and normalize_by_length against the golden the reference class produced (zero scores -> inf)."""
+    import inspect
+    from acoss_b200.chenfusion import ChenFusion
+    sig = inspect.signature(ChenFusion.__init__)
+    assert list(sig.parameters)[:10] == ["self", "dataset_csv", "datapath", "chroma_type", "shortname", "oti",
+                                         "kappa", "tau", "m", "downsample_fac"]
+    with open(os.path.join(os.path.dirname(__file__), "golden", "evalstats_golden.json")) as f:
+        n = json.load(f)["normalize_chen"]
+    c = ChenFusion(None, None, downsample_fac=1,
+                   features=[dict(hpcp=np.zeros((k, 12), np.float32), label="x") for k in n["n_frames"]])
+    assert c.name == "LateFusionChen" and list(c.Ds) == ["qmax", "dmax"]
+    Dq = np.floor(np.random.default_rng(n["seeds"][0]).random((9, 9)) * 60).astype(np.float32) * np.float32(0.5)
+    Dd = np.floor(np.random.default_rng(n["seeds"][1]).random((9, 9)) * 90).astype(np.float32) * np.float32(0.5)
+    np.fill_diagonal(Dq, 0); np.fill_diagonal(Dd, 0)
+    c.Ds["qmax"][:] = Dq; c.Ds["dmax"][:] = Dd
+    c.normalize_by_length()
+    for key in ("qmax", "dmax"):
+        want = np.array([[np.inf if x == "inf" else x for x in row] for row in n[key]], dtype=np.float32)
+        assert np.array_equal(np.asarray(c.Ds[key]), want)
+    with pytest.raises(NotImplementedError):               # SNF late fusion is outside the hot path
+        c.do_late_fusion()
