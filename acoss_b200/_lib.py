@@ -44,6 +44,8 @@ SIGNATURES = {
     "acoss_destroy": (C.c_int, [_vp]),
     "acoss_set_workspace_limit": (C.c_int, [_vp, C.c_int64]),
     "acoss_set_tracks": (C.c_int, [_vp, _fp, _i64p, C.c_int32, C.c_int]),
+    "acoss_set_tracks_raw": (C.c_int, [_vp, _fp, _i64p, C.c_int32, C.c_int32, _i64p]),
+    "acoss_get_tracks": (C.c_int, [_vp, _fp, C.c_int64]),
     "acoss_score_pairs": (C.c_int, [_vp, _i32p, C.c_int64, C.POINTER(Params), _fp]),
     "acoss_score_pairs_device": (C.c_int, [_vp, _i32p, C.c_int64, C.POINTER(Params), _fp]),
     "acoss_score_pairs_chen": (C.c_int, [_vp, _i32p, C.c_int64, C.POINTER(Params), _fp, _fp]),

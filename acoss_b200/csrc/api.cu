@@ -107,6 +107,8 @@ static int ensure(Buf &b, size_t bytes) {
 
 extern "C" {
 
+static int finish_tracks(acoss_ctx *c, const int64_t *offsets, int32_t n_tracks, int64_t mx, int64_t mn);
+
 void acoss_default_params(acoss_params *p) {
     if (!p) return;
     p->m = 9; p->tau = 1; p->kappa = 0.095f; p->oti = 1; p->noti = 12;
@@ -203,6 +205,12 @@ int acoss_set_tracks(acoss_ctx *c, const float *frames, const int64_t *offsets, 
         CUDA_TRY(cudaMemsetAsync(c->d_frames + total * NBINS, 0, 64 * sizeof(float), c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->d_frames, frames, (size_t)total * NBINS * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
+    return finish_tracks(c, offsets, n_tracks, mx, mn);
+}
+
+// common tail of acoss_set_tracks / acoss_set_tracks_raw: c->d_frames holds the frames (device), offsets on the host
+static int finish_tracks(acoss_ctx *c, const int64_t *offsets, int32_t n_tracks, int64_t mx, int64_t mn) {
+    const int64_t total = offsets[n_tracks];
     CUDA_TRY(cudaMalloc((void **)&c->d_offsets, (size_t)(n_tracks + 1) * sizeof(int64_t)));
     CUDA_TRY(cudaMalloc((void **)&c->d_gchroma, (size_t)n_tracks * NBINS * sizeof(float)));
     CUDA_TRY(cudaMemcpyAsync(c->d_offsets, offsets, (size_t)(n_tracks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
@@ -225,6 +233,64 @@ int acoss_set_tracks(acoss_ctx *c, const float *frames, const int64_t *offsets, 
         c->fx_exp = e;
     }
     if (((uintptr_t)c->d_frames & 15) != 0) c->fx_exp = -1000;   // vector loads need 16 B alignment
+    return ACOSS_OK;
+}
+
+int acoss_set_tracks_raw(acoss_ctx *c, const float *raw_frames, const int64_t *raw_offsets, int32_t n_tracks,
+                         int32_t downsample_fac, int64_t *offsets_out) {
+    if (!c || !raw_frames || !raw_offsets || n_tracks <= 0) { acoss_set_error("set_tracks_raw: bad arguments"); return ACOSS_E_INVALID; }
+    if (downsample_fac < 1 || downsample_fac > onramp_max_fac()) {
+        acoss_set_error("set_tracks_raw: downsample factor must be in 1..%d", onramp_max_fac());
+        return ACOSS_E_INVALID;
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (raw_offsets[0] != 0) { acoss_set_error("set_tracks_raw: offsets must start at 0"); return ACOSS_E_INVALID; }
+    std::vector<int64_t> off(n_tracks + 1, 0);
+    int64_t mx = 0, mn = INT64_MAX;
+    for (int t = 0; t < n_tracks; ++t) {
+        const int64_t n = raw_offsets[t + 1] - raw_offsets[t];
+        if (n < 0) { acoss_set_error("set_tracks_raw: offsets must be non-decreasing"); return ACOSS_E_INVALID; }
+        const int64_t no = (n + downsample_fac - 1) / downsample_fac;      // ceil(n / fac) blocks, last one short
+        off[t + 1] = off[t] + no;
+        mx = std::max(mx, no);
+        mn = std::min(mn, no);
+    }
+    if (mx > (1 << 20)) { acoss_set_error("set_tracks_raw: track longer than 2^20 frames"); return ACOSS_E_INVALID; }
+    const int64_t total_raw = raw_offsets[n_tracks], total = off[n_tracks];
+    if (c->own_frames && c->d_frames) CUDA_TRY(cudaFree(c->d_frames));
+    c->d_frames = nullptr;
+    if (c->d_offsets) CUDA_TRY(cudaFree(c->d_offsets));
+    if (c->d_gchroma) CUDA_TRY(cudaFree(c->d_gchroma));
+    c->d_offsets = nullptr; c->d_gchroma = nullptr;
+    float *d_raw = nullptr;
+    int64_t *d_roff = nullptr, *d_ooff = nullptr;
+    auto cleanup = [&]() { if (d_raw) cudaFree(d_raw); if (d_roff) cudaFree(d_roff); if (d_ooff) cudaFree(d_ooff); };
+#define CUDA_TRYC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { acoss_set_error("%s -> %s", #x, cudaGetErrorString(_e)); cleanup(); return _e == cudaErrorMemoryAllocation ? ACOSS_E_NOMEM : ACOSS_E_CUDA; } } while (0)
+    CUDA_TRYC(cudaMalloc((void **)&d_raw, (size_t)std::max<int64_t>(total_raw, 1) * NBINS * sizeof(float)));
+    CUDA_TRYC(cudaMalloc((void **)&d_roff, (size_t)(n_tracks + 1) * sizeof(int64_t)));
+    CUDA_TRYC(cudaMalloc((void **)&d_ooff, (size_t)(n_tracks + 1) * sizeof(int64_t)));
+    CUDA_TRYC(cudaMalloc((void **)&c->d_frames, (size_t)(total * NBINS + 64) * sizeof(float)));
+    c->own_frames = true;
+    CUDA_TRYC(cudaMemsetAsync(c->d_frames + total * NBINS, 0, 64 * sizeof(float), c->stream));
+    CUDA_TRYC(cudaMemcpyAsync(d_raw, raw_frames, (size_t)total_raw * NBINS * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRYC(cudaMemcpyAsync(d_roff, raw_offsets, (size_t)(n_tracks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRYC(cudaMemcpyAsync(d_ooff, off.data(), (size_t)(n_tracks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_median_sync(d_raw, d_roff, d_ooff, n_tracks, downsample_fac, total, c->d_frames, c->stream);
+    if (rc == ACOSS_OK) { cudaError_t e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) { acoss_set_error("median_sync: %s", cudaGetErrorString(e)); rc = ACOSS_E_CUDA; } }
+    cleanup();
+#undef CUDA_TRYC
+    if (rc != ACOSS_OK) return rc;
+    if (offsets_out) memcpy(offsets_out, off.data(), (size_t)(n_tracks + 1) * sizeof(int64_t));
+    return finish_tracks(c, off.data(), n_tracks, mx, mn);
+}
+
+int acoss_get_tracks(acoss_ctx *c, float *frames_out, int64_t total_frames) {
+    if (!c || !frames_out || !c->d_frames) { acoss_set_error("get_tracks: no tracks resident or NULL buffer"); return ACOSS_E_INVALID; }
+    if (total_frames != c->total_frames) { acoss_set_error("get_tracks: buffer holds %lld frames, resident set has %lld", (long long)total_frames, (long long)c->total_frames); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(frames_out, c->d_frames, (size_t)total_frames * NBINS * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ACOSS_OK;
 }
 
@@ -337,12 +403,16 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     uint32_t *status = (uint32_t *)c->status.p;
     for (int64_t first = 0; first < K; first += slots) {
         const int n = (int)std::min<int64_t>(slots, K - first);
+        ++c->stats[6];
         TRY(launch_pair_geometry(ts, pairs_dev, first, n, incr, (int32_t *)c->rows.p, (int32_t *)c->cols.p, st));
         ++launches;
         StageTimer t2(c, 1);
         if (fast) {
+            cudaEvent_t ea = nullptr, eb = nullptr;
+            if (c->profiling) { ea = get_event(c); eb = get_event(c); c->spans.push_back({3, ea, eb}); }
             TRY(launch_k2_fast(ts, pairs_dev, (const int32_t *)c->oti.p, first, n, *p, g, c->fast.p, fast_slot,
-                               (uint32_t *)c->crp.p, (float *)c->thr_q.p, (float *)c->thr_r.p, status, (uint32_t *)c->dbg.p, st, &launches));
+                               (uint32_t *)c->crp.p, (float *)c->thr_q.p, (float *)c->thr_r.p, status, (uint32_t *)c->dbg.p, st, &launches,
+                               ea, eb));
             // exact fallback for pairs the fast path flagged: compact their slot ids, re-run in groups
             TRY(ensure(c->fbmap, (size_t)slots * 4 + 64));
             int nfb = 0;

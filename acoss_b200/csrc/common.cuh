@@ -64,6 +64,9 @@ __device__ __forceinline__ double acc_f32prod(double acc, float a, float b) {
 // host launchers (one per translation unit) -----------------------------------------------------
 struct Params;   // fwd
 
+int onramp_max_fac();
+int launch_median_sync(const float *raw, const int64_t *raw_off, const int64_t *out_off, int n_tracks, int fac,
+                       int64_t total_out, float *out, cudaStream_t st);
 int launch_global_chroma(const float *frames, const int64_t *offsets, int n_tracks, float *gchroma,
                          cudaStream_t st);
 int launch_frame_stats(const float *frames, int64_t total_frames, float *stats2, cudaStream_t st);

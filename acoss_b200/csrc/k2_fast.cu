@@ -35,8 +35,8 @@ constexpr int NBIN = 64;            // histogram bins per level (+ one underflow
 constexpr int SPARSE_CAP = 512;     // live lines per pair and orientation the sparse refinement can take
 constexpr int SBIN = 256;           // bins of the per-line sample histogram (select kernel)
 constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
-constexpr int CAND_CAP = 64;        // candidates per row / column
-constexpr int BRACKET_TARGET = 48;  // a bracket holding more cells than this is split by another histogram level
+constexpr int CAND_CAP = 128;       // candidates per row / column
+constexpr int BRACKET_TARGET = 96;  // a bracket holding more cells than this is split by another histogram level
 constexpr int WPC = 4;              // warps per CTA in the sweep kernels
 constexpr int RCV = 4;              // owned frames per lane (register columns) in the sweep kernels
 
@@ -1111,7 +1111,8 @@ size_t k2_fast_slot_bytes(const SlotGeom &g, int max_frames) { return make_layou
 
 int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti, int64_t first, int n,
                    const acoss_params &p, const SlotGeom &g, void *scratch, size_t slot_bytes, uint32_t *crp,
-                   float *thr_q, float *thr_r, uint32_t *status, uint32_t *dbg, cudaStream_t st, int64_t *launches) {
+                   float *thr_q, float *thr_r, uint32_t *status, uint32_t *dbg, cudaStream_t st, int64_t *launches,
+                   cudaEvent_t emit_begin, cudaEvent_t emit_end) {
     if (n <= 0) return ACOSS_OK;
     constexpr int RC = RCV;
     const FastLayout L = make_layout(g, ts.max_frames);
@@ -1163,8 +1164,10 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
         fast_sparse_kernel<<<(unsigned)((warps + WPC - 1) / WPC), 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, magic, status, dbg + 8);
         CUDA_TRY(cudaGetLastError());
     }
+    if (emit_begin) CUDA_TRY(cudaEventRecord(emit_begin, st));
     fast_emit_kernel<RC><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
     CUDA_TRY(cudaGetLastError());
+    if (emit_end) CUDA_TRY(cudaEventRecord(emit_end, st));
     fast_scatter_kernel<<<dim3(strips_c, n), 128, 0, st>>>(n, L, base, first, status, dbg);
     CUDA_TRY(cudaGetLastError());
     fast_resolve_thr_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(ts, pairs, first, n, L, base, p.integer_guard, unit,

@@ -80,6 +80,29 @@ class Engine:
         self.n_tracks = n
         self.offsets = offsets
 
+    def set_tracks_raw(self, raw_frames, raw_offsets, downsample_fac: int) -> np.ndarray:
+        """Raw (not yet downsampled) chroma frames -> GPU median downsampling (acoss_set_tracks_raw, the
+        aggregation of rqa_serra09.py:47-53) -> resident track set.  Returns the downsampled offsets."""
+        raw_offsets = np.ascontiguousarray(raw_offsets, dtype=np.int64)
+        raw_frames = np.ascontiguousarray(raw_frames, dtype=np.float32)
+        n = len(raw_offsets) - 1
+        if raw_frames.size != int(raw_offsets[-1]) * 12:
+            raise ValueError("frames size does not match offsets")
+        out_off = np.zeros(n + 1, dtype=np.int64)
+        check(self._lib.acoss_set_tracks_raw(self._ctx, raw_frames.ctypes.data, raw_offsets.ctypes.data, n,
+                                             int(downsample_fac), out_off.ctypes.data))
+        self._keepalive = None
+        self.n_tracks = n
+        self.offsets = out_off
+        return out_off
+
+    def get_tracks(self) -> np.ndarray:
+        """The resident (post-downsampling) frames, float32 (total, 12)."""
+        total = int(self.offsets[-1])
+        out = np.empty((total, 12), dtype=np.float32)
+        check(self._lib.acoss_get_tracks(self._ctx, out.ctypes.data, total))
+        return out
+
     # -- scoring --------------------------------------------------------------------------------
     def score_pairs(self, pairs, params: Params | None = None) -> np.ndarray:
         """Host in / host out (the end-to-end path): pairs (K, 2) int -> scores float32 (K,)."""
@@ -172,7 +195,7 @@ class Engine:
         """Accumulated CUDA-event milliseconds per pipeline stage since set_profiling(True)."""
         ms = np.zeros(4, dtype=np.float64)
         check(self._lib.acoss_stage_ms(self._ctx, ms.ctypes.data))
-        return dict(k1_oti=float(ms[0]), k2_crp=float(ms[1]), k3_dp=float(ms[2]))
+        return dict(k1_oti=float(ms[0]), k2_crp=float(ms[1]), k3_dp=float(ms[2]), k2_emit=float(ms[3]))
 
     def debug_counters(self) -> dict:
         """Diagnostic counters of the last scoring call (acoss_debug_counters): dense histogram level per
@@ -190,4 +213,4 @@ class Engine:
         st = np.zeros(8, dtype=np.int64)
         check(self._lib.acoss_last_stats(self._ctx, st.ctypes.data))
         return dict(pairs=int(st[0]), fallback_pairs=int(st[1]), launches=int(st[2]), cells=int(st[3]),
-                    exact_cells=int(st[4]), status_or=int(st[5]))
+                    exact_cells=int(st[4]), status_or=int(st[5]), chunks=int(st[6]))

@@ -58,6 +58,7 @@ class Serra09(CoverAlgorithm):
         self.tile_pairs = int(tile_pairs)
         self.device = device
         self.crp_path = _lib.CRP_AUTO              # ACOSS_CRP_AUTO (fast path) / ACOSS_CRP_EXACT
+        self.gpu_onramp = True                     # downsample_fac > 1: median aggregation on the GPU
         self.all_feats = {}                      # cached (downsampled) chroma per song
         self._engine = engine
         self._resident = False
@@ -86,9 +87,22 @@ class Serra09(CoverAlgorithm):
         if self._engine is None:
             self._engine = Engine(self.device)
         if not self._resident:
-            tracks = [np.asarray(self.load_features(i), dtype=np.float32) for i in range(self.N)]
-            frames, offsets = pack_tracks(tracks)
-            self._engine.set_tracks(frames, offsets)
+            if self.gpu_onramp and 1 < int(self.downsample_fac) <= 128:
+                # the median aggregation of load_features runs on the GPU (k0_onramp.cu): raw frames go up once,
+                # the downsampled tracks stay resident and are mirrored into the host cache all_feats
+                raws = []
+                for i in range(self.N):
+                    feats = CoverAlgorithm.load_features(self, i)         # also fills self.cliques
+                    raws.append(np.asarray(feats[self.chroma_type], dtype=np.float32))
+                frames, offsets = pack_tracks(raws)
+                out_off = self._engine.set_tracks_raw(frames, offsets, int(self.downsample_fac))
+                ds = self._engine.get_tracks()
+                for i in range(self.N):
+                    self.all_feats.setdefault(i, ds[out_off[i]:out_off[i + 1]])
+            else:
+                tracks = [np.asarray(self.load_features(i), dtype=np.float32) for i in range(self.N)]
+                frames, offsets = pack_tracks(tracks)
+                self._engine.set_tracks(frames, offsets)
             self._resident = True
         return self._engine
 

@@ -85,6 +85,16 @@ int acoss_set_workspace_limit(acoss_ctx *ctx, int64_t bytes);
 int acoss_set_tracks(acoss_ctx *ctx, const float *frames, const int64_t *offsets, int32_t n_tracks,
                      int frames_on_device);
 
+/* The same from RAW (not yet downsampled) chroma features: replaces the median aggregation of
+ * Serra09.load_features (rqa_serra09.py:47-53, librosa.util.sync with aggregate=np.median): output frame k
+ * of a track is the per-bin median of raw frames [fac*k, min(fac*k+fac, n)), float32, computed on the GPU,
+ * and the downsampled tracks become the resident set.  raw_frames / raw_offsets: host memory, layout as
+ * above.  offsets_out (may be NULL, n_tracks + 1 entries) receives the downsampled offsets.  fac in 1..128. */
+int acoss_set_tracks_raw(acoss_ctx *ctx, const float *raw_frames, const int64_t *raw_offsets, int32_t n_tracks,
+                         int32_t downsample_fac, int64_t *offsets_out);
+/* Copies the resident (post-downsampling) frames back to the host: total_frames * 12 floats. */
+int acoss_get_tracks(acoss_ctx *ctx, float *frames_out, int64_t total_frames);
+
 /* Replaces Serra09.similarity(idxs) (rqa_serra09.py:55-69) for a whole batch: pairs[2k] = query
  * track, pairs[2k+1] = reference track; scores[k] = the float the reference stores in
  * Ds[key][i][j].  Host buffers; H2D of the pair list and D2H of the scores happen inside. */
@@ -131,7 +141,8 @@ int acoss_knn_sw(acoss_ctx *ctx, const double *csms, const int64_t *offsets, con
                  const int32_t *nn, int64_t n_mats, float *scores, uint32_t *bits_out);
 
 /* Counters of the last acoss_score_pairs* call: [0] pairs, [1] pairs that took the exact
- * fallback, [2] kernel launches, [3] cells (sum of M'*N'), [4] exact re-evaluated candidate cells. */
+ * fallback, [2] kernel launches, [3] cells (sum of M'*N'), [4] exact re-evaluated candidate cells, [5] OR of the
+ * per-pair status words, [6] slot chunks the call was processed in (= launches of each K2 / K3 kernel). */
 int acoss_last_stats(acoss_ctx *ctx, int64_t stats[8]);
 
 /* Diagnostic counters of the last acoss_score_pairs* call (valid after acoss_sync).  Dense histogram
@@ -144,7 +155,8 @@ int acoss_debug_counters(acoss_ctx *ctx, int64_t out[32]);
 
 /* Per-stage device timing of the pair pipeline, measured with CUDA events on the context stream:
  * acoss_set_profiling(ctx, 1) resets and enables it; acoss_stage_ms returns the accumulated
- * milliseconds of [0] K1 OTI, [1] K2 CRP construction, [2] K3 alignment DP, [3] reserved. */
+ * milliseconds of [0] K1 OTI, [1] K2 CRP construction, [2] K3 alignment DP, [3] the emit sweep alone
+ * (fast_emit_kernel, the dominant kernel of K2; part of [1]). */
 int acoss_set_profiling(acoss_ctx *ctx, int on);
 int acoss_stage_ms(acoss_ctx *ctx, double ms[4]);
 

@@ -148,3 +148,41 @@ def test_chenfusion_dropin(workdir):
     assert np.array_equal(np.array(c.Ds["dmax"]), want)
     c.cleanup_memmap()
     c.close()
+
+
+def test_gpu_median_onramp_bit_exact():
+    """acoss_set_tracks_raw == librosa.util.sync(..., aggregate=np.median) restated by median_sync (np.median on
+    float32 blocks): full, short-last and single-frame blocks, odd and even block sizes, ties, several factors."""
+    from acoss_b200 import Engine, pack_tracks
+    from acoss_b200.serra09 import median_sync
+    rng = np.random.default_rng(12)
+    raws = [rng.random((int(n), 12)).astype(np.float32) for n in (2000, 2401, 1810, 41, 40, 39, 1, 81, 517)]
+    raws.append(np.round(rng.random((333, 12)) * 4).astype(np.float32) / np.float32(4))       # many ties
+    frames, offs = pack_tracks(raws)
+    with Engine(0) as eng:
+        for fac in (40, 7, 2, 1, 128):
+            out_off = eng.set_tracks_raw(frames, offs, fac)
+            got = eng.get_tracks()
+            want = [median_sync(r, fac) for r in raws]
+            assert list(np.diff(out_off)) == [len(w) for w in want]
+            assert np.array_equal(got, np.concatenate(want)), fac
+        from acoss_b200 import AcossError
+        with pytest.raises(AcossError):
+            eng.set_tracks_raw(frames, offs, 129)
+
+
+def test_serra09_gpu_onramp_equals_host_onramp(workdir):
+    """The plugin's GPU on-ramp (default) and the host median give identical scores and cached features."""
+    from acoss_b200.serra09 import Serra09, median_sync
+    rng = np.random.default_rng(6)
+    raw = [rng.random((int(n), 12)).astype(np.float32) for n in (2000, 2400, 1810, 2222)]
+    idx = np.array([[0, 1], [0, 2], [1, 2], [2, 3]])
+    a = Serra09(None, None, features=[dict(hpcp=r, label="a") for r in raw], shortname="gpuramp")
+    a.similarity(idx)
+    b = Serra09(None, None, features=[dict(hpcp=r, label="a") for r in raw], shortname="hostramp")
+    b.gpu_onramp = False
+    b.similarity(idx)
+    assert np.array_equal(np.array(a.Ds["main"]), np.array(b.Ds["main"]))
+    for i, r in enumerate(raw):
+        assert np.array_equal(a.load_features(i), median_sync(r, 40))
+    a.close(); b.close()
