@@ -760,8 +760,8 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, c
 // ------------------------------------------------------------------------------------------------
 // emit sweep (orientation 0: owned = reference columns, streamed = query rows)
 // ------------------------------------------------------------------------------------------------
-template <int RC>
-__global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+template <int RC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
                                                              uint32_t *__restrict__ crp_all, int words,
@@ -1165,7 +1165,9 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
         CUDA_TRY(cudaGetLastError());
     }
     if (emit_begin) CUDA_TRY(cudaEventRecord(emit_begin, st));
-    fast_emit_kernel<RC><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
+    static const bool emit4 = getenv("ACOSS_EMIT_MINB4") != nullptr;        // tuning switch: 4 CTAs / SM (128 registers)
+    if (emit4) fast_emit_kernel<RC, 4><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
+    else fast_emit_kernel<RC, 3><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
     CUDA_TRY(cudaGetLastError());
     if (emit_end) CUDA_TRY(cudaEventRecord(emit_end, st));
     fast_scatter_kernel<<<dim3(strips_c, n), 128, 0, st>>>(n, L, base, first, status, dbg);

@@ -37,8 +37,8 @@ sys.path.insert(0, ROOT)
 
 # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (dram__bytes_read.sum +
 # dram__bytes_write.sum of one fast_emit_kernel launch, divided by the pairs of that launch)
-EMIT_DRAM_BYTES_PER_PAIR = 1.99e6
-EMIT_TRAFFIC_SOURCE = "profiles/r1_k2_s4.md (2048-pair launch: 1.58 GB read + 2.49 GB written)"
+EMIT_DRAM_BYTES_PER_PAIR = 1.836e6
+EMIT_TRAFFIC_SOURCE = "profiles/r1_k2_s10.md (2048-pair launch: 1.62 GB read + 2.14 GB written)"
 
 METRIC = "all-pairs alignments/sec"
 UNIT = "pairs/s"
