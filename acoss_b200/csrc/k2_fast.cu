@@ -421,13 +421,15 @@ __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict
         constexpr int U = decltype(uc)::value;
         constexpr bool CALL = decltype(callc)::value, PF = decltype(pfc)::value;
         int eb[RC];
+        PT pn{};
+        if (PF) pn = __ldg(pp + a + 1);            // next row's parameter: a whole row ahead of its use
         sw.dot(c0, c1, c2, eb);
         // the frame registers are dead now: refill them with the next row while this row finishes
         px += 3;
         c0 = __ldg(px); c1 = __ldg(px + 1); c2 = __ldg(px + 2);
         sw.template finish<U>(eb);
         if (CALL) fn(a, pc);
-        if (PF) pc = __ldg(pp + a + 1);
+        if (PF) pc = pn;
         ++a;
     };
     // rows 0..8: the diagonal sums fill up; only row 8 produces a window
