@@ -767,8 +767,8 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, c
 // ------------------------------------------------------------------------------------------------
 // emit sweep (orientation 0: owned = reference columns, streamed = query rows)
 // ------------------------------------------------------------------------------------------------
-template <int RC, int MINB>
-__global__ void __launch_bounds__(32 * WPC, MINB) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+template <int RC>
+__global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
                                                              uint32_t *__restrict__ crp_all, int words,
@@ -1137,7 +1137,10 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     const int strips_c = (g.max_cols + outw - 1) / outw, strips_r = (g.max_rows + outw - 1) / outw;
     const size_t smem = (size_t)WPC * (NBIN + 2) * (RC / 2) * 32 * 4;
     const size_t smem_sel = (size_t)(SBIN / 2) * SEL_THREADS * 4;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};                  // function attributes are per device
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    bool &attr_done = attr_done_dev[dev & 63];
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1172,9 +1175,8 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
         CUDA_TRY(cudaGetLastError());
     }
     if (emit_begin) CUDA_TRY(cudaEventRecord(emit_begin, st));
-    static const bool emit4 = getenv("ACOSS_EMIT_MINB4") != nullptr;        // tuning switch: 4 CTAs / SM (128 registers)
-    if (emit4) fast_emit_kernel<RC, 4><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
-    else fast_emit_kernel<RC, 3><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
+    // 3 CTAs / SM (168 registers): 4 CTAs (128 registers, spills) measured 3 % slower
+    fast_emit_kernel<RC><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
     CUDA_TRY(cudaGetLastError());
     if (emit_end) CUDA_TRY(cudaEventRecord(emit_end, st));
     fast_scatter_kernel<<<dim3(strips_c, n), 128, 0, st>>>(n, L, base, first, status, dbg);

@@ -364,6 +364,147 @@ __global__ void __launch_bounds__(128) dp_dmax_kernel(const uint32_t *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dmax, packed: exact integer DP in signed 16-bit pairs for essentia's default gamma_o = gamma_e = 0.5 with
+// Chen's bridging terms, scores scaled x2:
+//   D2 = relu(max5 + (c ? +2 : -1)),  max5 over A[c-1], B[c-1] + 2 b(u-1,c), A[c-2] + 2 b(u,c-1),
+//                                      C[c-1] + 2 (b(u-2,c) + b(u-1,c)), A[c-3] + 2 (b(u,c-2) + b(u,c-1))
+// (A, B, C = rows u-1, u-2, u-3).  Every move gains at most rows + columns advanced - 1, so D <= R + C and
+// D2 fits int16 while 2 (R + C) <= 32000.  Same register layout as dp_packed_kernel (register t of a
+// 32-column group = columns t, t+16); the new row is written over the oldest one (C), t descending.
+// Cells right of the matrix (pad bits 0) never exceed the largest real cell: by induction a pad cell is
+// relu(max5 - 1) with zero bridging bits in its own column, and every candidate it sees is matched or beaten
+// by the real cell left of it (a hit there adds 2) -- so no column mask is needed for the maximum.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmax_group_row(const uint32_t (&A)[16], const uint32_t (&B)[16], uint32_t (&C)[16],
+                                               uint32_t hA1, uint32_t hA2, uint32_t hA3, uint32_t hB1, uint32_t hC1,
+                                               uint32_t w0, uint32_t w1, uint32_t w2, uint32_t pw0, uint32_t ppw0,
+                                               uint32_t &best) {
+    constexpr uint32_t M = 0x00010001u;
+#pragma unroll
+    for (int t = 15; t >= 0; --t) {
+        const uint32_t a1 = (t >= 1) ? A[t - 1] : hA1;
+        const uint32_t a2 = (t >= 2) ? A[t - 2] : (t == 1 ? hA1 : hA2);
+        const uint32_t a3 = (t >= 3) ? A[t - 3] : (t == 2 ? hA1 : (t == 1 ? hA2 : hA3));
+        const uint32_t b1 = (t >= 1) ? B[t - 1] : hB1;
+        const uint32_t c1 = (t >= 1) ? C[t - 1] : hC1;
+        const uint32_t v0 = (w0 >> t) & M;                     // b(u, c)
+        const uint32_t xu1 = (w1 >> t) & M, xu2 = (w2 >> t) & M;   // b(u, c-1), b(u, c-2)
+        const uint32_t xp = (pw0 >> t) & M, xpp = (ppw0 >> t) & M; // b(u-1, c), b(u-2, c)
+        const uint32_t c2 = b1 + 2u * xp;                      // halves stay < 2^15: no carry between them
+        const uint32_t c3 = a2 + 2u * xu1;
+        const uint32_t c4 = c1 + 2u * (xpp + xp);
+        const uint32_t c5 = a3 + 2u * (xu2 + xu1);
+        const uint32_t m5 = __vimax3_s16x2(__vimax3_s16x2(a1, c2, c3), c4, c5);
+        const uint32_t msk = v0 * 0xffffu;
+        const uint32_t w = (msk & 0x00020002u) | ~msk;         // +2 on a hit, -1 otherwise
+        const uint32_t sres = __viaddmax_s16x2_relu(m5, w, 0u);
+        best = __vmaxs2(best, sres);
+        C[t] = sres;
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) dp_dmax_packed_kernel(const uint32_t *__restrict__ bits_all, int64_t slot_words,
+                                                             int wpr, const int32_t *__restrict__ rows_a,
+                                                             const int32_t *__restrict__ cols_a, int n,
+                                                             float *__restrict__ scores, uint2 *__restrict__ halo_all,
+                                                             int64_t halo_pitch) {
+    const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pair >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int R = rows_a[pair], C = cols_a[pair];
+    if (R < 4 || C < 4) {
+        if (lane == 0) scores[pair] = 0.f;
+        return;
+    }
+    const uint32_t *bits = bits_all + (int64_t)pair * slot_words;
+    constexpr int W = 1024 * G;                  // DP columns per strip (DP column d = CRP column d + 3)
+    const int nstrips = (C - 3 + W - 1) / W;
+    uint2 *halo0 = halo_all + (int64_t)pair * 2 * halo_pitch;
+    uint32_t best = 0u;
+    for (int s = 0; s < nstrips; ++s) {
+        const int wbase = s * 32 * G + lane * G;            // first CRP word of this lane's chunk
+        const uint2 *halo_in = halo0 + (int64_t)(s & 1) * halo_pitch;
+        uint2 *halo_out = halo0 + (int64_t)((s + 1) & 1) * halo_pitch;
+        const bool write_halo = (s + 1 < nstrips);
+        uint32_t Wd[G + 1];
+        auto load_row = [&](int u, uint32_t (&dst)[G + 1]) {
+            const uint32_t *row = bits + (int64_t)u * wpr;
+#pragma unroll
+            for (int g = 0; g <= G; ++g) {
+                const int w = wbase + g;
+                dst[g] = (w < wpr) ? __ldg(row + w) : 0u;
+            }
+        };
+        uint32_t A[G][16], B[G][16], Cc[G][16];
+        uint32_t pw0[G], ppw0[G];
+        {
+            uint32_t T1[G + 1], T2[G + 1];
+            load_row(1, T1);
+            load_row(2, T2);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                ppw0[g] = __funnelshift_r(T1[g], T1[g + 1], 3);
+                pw0[g] = __funnelshift_r(T2[g], T2[g + 1], 3);
+#pragma unroll
+                for (int t = 0; t < 16; ++t) { A[g][t] = 0u; B[g][t] = 0u; Cc[g][t] = 0u; }
+            }
+        }
+        // lane 0: (D2[c0-2] | D2[c0-1] << 16, D2[c0-3]) of rows u-1, u-2, u-3 at the strip's left edge; rows < 3 are zero
+        uint2 h1 = make_uint2(0u, 0u), h2 = h1, h3 = h1;
+        load_row(3, Wd);
+
+        auto row_step = [&](int u, uint32_t (&Ar)[G][16], uint32_t (&Br)[G][16], uint32_t (&Cr)[G][16]) {
+            uint32_t nA15 = __shfl_up_sync(0xffffffffu, Ar[G - 1][15], 1);
+            uint32_t nA14 = __shfl_up_sync(0xffffffffu, Ar[G - 1][14], 1);
+            uint32_t nA13 = __shfl_up_sync(0xffffffffu, Ar[G - 1][13], 1);
+            uint32_t nB15 = __shfl_up_sync(0xffffffffu, Br[G - 1][15], 1);
+            uint32_t nC15 = __shfl_up_sync(0xffffffffu, Cr[G - 1][15], 1);
+            if (lane == 0) { nA15 = h1.x; nA14 = h1.x << 16; nA13 = h1.y << 16; nB15 = h2.x; nC15 = h3.x; }
+            uint32_t hA1[G], hA2[G], hA3[G], hB1[G], hC1[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                hA1[g] = lohi((g == 0) ? nA15 : Ar[g - 1][15], Ar[g][15]);
+                hA2[g] = lohi((g == 0) ? nA14 : Ar[g - 1][14], Ar[g][14]);
+                hA3[g] = lohi((g == 0) ? nA13 : Ar[g - 1][13], Ar[g][13]);
+                hB1[g] = lohi((g == 0) ? nB15 : Br[g - 1][15], Br[g][15]);
+                hC1[g] = lohi((g == 0) ? nC15 : Cr[g - 1][15], Cr[g][15]);
+            }
+            uint32_t cur[G + 1];
+#pragma unroll
+            for (int g = 0; g <= G; ++g) cur[g] = Wd[g];
+            if (u + 1 < R) load_row(u + 1, Wd);                 // prefetch next row's CRP words
+            const uint2 hnew = (lane == 0 && s > 0) ? halo_in[u] : make_uint2(0u, 0u);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint32_t w0 = __funnelshift_r(cur[g], cur[g + 1], 3), w1 = __funnelshift_r(cur[g], cur[g + 1], 2),
+                               w2 = __funnelshift_r(cur[g], cur[g + 1], 1);
+                dmax_group_row(Ar[g], Br[g], Cr[g], hA1[g], hA2[g], hA3[g], hB1[g], hC1[g], w0, w1, w2, pw0[g], ppw0[g], best);
+                ppw0[g] = pw0[g];
+                pw0[g] = w0;
+            }
+            if (write_halo && lane == 31)
+                halo_out[u] = make_uint2(__byte_perm(Cr[G - 1][14], Cr[G - 1][15], 0x7632), Cr[G - 1][13] >> 16);
+            h3 = h2; h2 = h1; h1 = hnew;
+        };
+
+        int u = 3;
+        for (; u + 2 < R; u += 3) {
+            row_step(u, A, B, Cc);          // new row -> Cc
+            row_step(u + 1, Cc, A, B);      // new row -> B
+            row_step(u + 2, B, Cc, A);      // new row -> A
+        }
+        if (u < R) { row_step(u, A, B, Cc); ++u; }
+        if (u < R) { row_step(u, Cc, A, B); ++u; }
+        __syncwarp();
+    }
+    int bm = max((int)(short)(best & 0xffffu), (int)(short)(best >> 16));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) bm = max(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+    if (lane == 0) scores[pair] = (float)bm * 0.5f;
+}
+
+// ------------------------------------------------------------------------------------------------
 // helpers: pair geometry, byte-matrix packing
 // ------------------------------------------------------------------------------------------------
 __global__ void pair_geometry_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n, int incr,
@@ -466,6 +607,17 @@ int launch_dp_bits(const uint32_t *bits, int64_t slot_words, int words_per_row, 
                                         halo_pitch, st);
     }
     const int blocks = (n + 3) / 4;
+    if (mode == ACOSS_ALIGN_DMAX && gamma_o == 0.5f && gamma_e == 0.5f && 2L * ((long)max_rows + max_cols) <= 32000L) {
+        const int dpcols = max_cols - 3;
+        if (dpcols <= 1024 || (dpcols > 2048 && dpcols <= 3072))   // least padded strip layout of 1024 / 2048 columns
+            dp_dmax_packed_kernel<1><<<blocks, 128, 0, st>>>(bits, slot_words, words_per_row, rows, cols, n, scores,
+                                                             (uint2 *)halo_scratch, halo_pitch);
+        else
+            dp_dmax_packed_kernel<2><<<blocks, 128, 0, st>>>(bits, slot_words, words_per_row, rows, cols, n, scores,
+                                                             (uint2 *)halo_scratch, halo_pitch);
+        CUDA_TRY(cudaGetLastError());
+        return ACOSS_OK;
+    }
     if (mode == ACOSS_ALIGN_QMAX)
         dp_scalar_kernel<MODE_QMAX><<<blocks, 128, 0, st>>>(bits, slot_words, words_per_row, rows, cols, n, gamma_o,
                                                             gamma_e, scores, (float4 *)halo_scratch, halo_pitch);
