@@ -970,7 +970,8 @@ __device__ __forceinline__ float exact_item(const float *__restrict__ Q, const f
     return __fadd_rn(__fsub_rn(aa, __fmul_rn(2.f, (float)acc)), bb);
 }
 
-// one 8-lane group per line (row or column)
+// 32 lines (rows, then columns) per CTA.  Phase 1 walks the CTA's candidates as one flat list, so every thread
+// evaluates the same number of cells whatever the lines' counts are; phase 2 ranks with one 8-lane group per line.
 __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                                int64_t first, int n, FastLayout L,
                                                                char *__restrict__ scratch, int guard, double unit,
@@ -979,10 +980,14 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
                                                                uint32_t *__restrict__ status) {
     __shared__ float s_item[32][CAND_CAP];
     __shared__ float s_sel[32][4];
+    __shared__ int s_pref[33];                                // exclusive prefix of the lines' candidate counts
+    __shared__ int s_nbelow[32];
+    __shared__ int s_nan;
     const int slot = blockIdx.y;
     if (slot >= n) return;
     const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
-    const int gline = blockIdx.x * 32 + grp;                  // 0 .. Mx+Nx-1 (rows then columns)
+    const int gline0 = blockIdx.x * 32;
+    const int gline = gline0 + grp;                           // 0 .. Mx+Nx-1 (rows then columns)
     const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
     const int Mx = h->Mx, Nx = h->Nx;
     const bool live = gline < Mx + Nx;
@@ -998,6 +1003,43 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
     const uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
     float *candd = slot_ptr<float>(scratch, L, slot, L.off_candd);
     const unsigned gmask = 0xffu << (8 * ((threadIdx.x & 31) >> 3));
+    if (threadIdx.x < 32) {                                   // warp 0: counts of the CTA's 32 lines and their prefix
+        const int gl = gline0 + threadIdx.x;
+        int c = 0;
+        if (gl < Mx + Nx) c = (int)min(cnt_a[gl < Mx ? gl : L.max_rows + gl - Mx], (unsigned)CAND_CAP);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += v;
+        }
+        s_pref[threadIdx.x + 1] = incl;
+        if (threadIdx.x == 0) { s_pref[0] = 0; s_nan = 0; }
+        s_nbelow[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    const int total = s_pref[32];
+    for (int wi = threadIdx.x; wi < total; wi += 256) {
+        int g = 0;                                            // largest g with s_pref[g] <= wi
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1)
+            if (s_pref[g + o] <= wi) g += o;
+        const int p = wi - s_pref[g];
+        const int gl = gline0 + g;
+        const bool rw = gl < Mx;
+        const int ix = rw ? gl : gl - Mx;
+        const int ln = rw ? ix : L.max_rows + ix;
+        const unsigned e = cand[(size_t)ln * CAND_CAP + p];
+        const int other = e & 0x7fff;
+        const int i = rw ? ix : other, j = rw ? other : ix;
+        const float item = exact_item(Q, R, i, j, aaf[i], bbf[j]);
+        const float d = __fsqrt_rn(item);
+        if (d != d) s_nan = 1;
+        candd[(size_t)ln * CAND_CAP + p] = d;
+        s_item[g][p] = item;
+        if (e >> 15) atomicAdd(&s_nbelow[g], 1);
+    }
+    __syncthreads();
     int cnt = 0;
     bool over = false;
     if (live) {
@@ -1005,22 +1047,8 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
         over = c > CAND_CAP;
         cnt = (int)min(c, (unsigned)CAND_CAP);
     }
-    int nbelow = 0;
-    bool nan = false;
-    for (int p = sub; p < cnt; p += 8) {
-        const unsigned e = cand[(size_t)line * CAND_CAP + p];
-        const int other = e & 0x7fff;
-        const int i = isrow ? idx : other, j = isrow ? other : idx;
-        const float item = exact_item(Q, R, i, j, aaf[i], bbf[j]);
-        const float d = __fsqrt_rn(item);
-        nan |= (d != d);
-        candd[(size_t)line * CAND_CAP + p] = d;
-        s_item[grp][p] = item;
-        nbelow += (e >> 15) & 1;
-    }
-#pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) nbelow += __shfl_xor_sync(gmask, nbelow, o, 8);
-    __syncwarp(gmask);
+    const int nbelow = s_nbelow[grp];
+    const bool nan = (s_nan != 0) && (threadIdx.x == 0);
     if (!live) return;
     if (nan) atomicOr(&status[k], PAIR_ST_NAN);
     const int side = isrow ? 0 : 1;
