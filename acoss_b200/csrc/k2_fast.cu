@@ -301,10 +301,17 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(int n, FastLay
     const int lo1 = h->lo1, hi1 = h->hi1;
     int shs = 0;
     while ((((int64_t)hi1 - lo1) >> shs) > SBIN - 1) ++shs;
-    for (int t = 0; t < ns; ++t) {
-        const int z = samp[(int64_t)t * pitch + idx];
-        const int b = min(max((z - lo1) >> shs, 0), SBIN - 1);
-        hist[(b >> 1) * SEL_THREADS] += 1u << (16 * (b & 1));
+    for (int t0 = 0; t0 < ns; t0 += 8) {                      // 8 independent loads in flight per thread
+        int z[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) z[u] = (t0 + u < ns) ? __ldg(samp + (int64_t)(t0 + u) * pitch + idx) : 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (t0 + u < ns) {
+                const int b = min(max((z[u] - lo1) >> shs, 0), SBIN - 1);
+                hist[(b >> 1) * SEL_THREADS] += 1u << (16 * (b & 1));
+            }
+        }
     }
     // wanted ranks floor(k) .. ceil(k) of Lother entries -> sample ranks mu -+ 4.5 sigma
     const float pq = ((float)h->fk[side] + 0.5f) / (float)Lother;
@@ -321,6 +328,7 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(int n, FastLay
         if (b_lo < 0 && cum + c1 > r_lo) b_lo = 2 * b + 1;
         if (b_hi < 0 && cum + c1 > r_hi) b_hi = 2 * b + 1;
         cum += c1;
+        if (b_hi >= 0) break;                                 // both ranks located (r_lo <= r_hi)
     }
     int lo = lo1, hi = hi1;
     // short lines have too few samples to steer anything: a 64-bin split of the whole item range already

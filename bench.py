@@ -126,7 +126,7 @@ def run_reference(args, rank, world):
     from oracle import serra09_c as oc
     tracks, labels, frames, offs, pairs, lens = build_dataset()
     cores = os.cpu_count() or 1
-    per_step = max(cores, 8)
+    per_step = 4 * max(cores, 8)                               # a few seconds of CPU per step
     rng = np.random.default_rng(1234)
     sel = rng.permutation(len(pairs))
     p = oc.params()
@@ -308,7 +308,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import serra09_c as oc
         cores = os.cpu_count() or 1
-        n_s = args.cpu_sample or max(cores, 8) * 3
+        n_s = args.cpu_sample or max(cores, 8) * 10              # about 10-15 s of CPU work
         idx = timed[np.random.default_rng(5).permutation(len(timed))[:n_s]]
         tc0 = time.perf_counter()
         ref_scores = oc.pairs(frames, offs, idx, oc.params(), nthreads=cores)
