@@ -122,3 +122,47 @@ def pair_cells(lengths, pairs, incr: int = 9) -> int:
     ln = np.asarray(lengths, dtype=np.int64) - incr
     p = np.asarray(pairs)
     return int((ln[p[:, 0]] * ln[p[:, 1]]).sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# EarlyFusion block features (what EarlyFusion.load_features returns, earlyfusion_traile.py:66-155)
+# ---------------------------------------------------------------------------------------------
+EF_DIMS = dict(mfccs=20 * 50, ssms=50 * 49 // 2, chromas=12 * 40)     # reference defaults: 1000, 1225, 480
+
+
+def ef_dataset(cliques, n_blocks: int, seed: int, dims=None, dtype=np.float32, jitter: float = 0.15):
+    """Synthetic beat-synchronous block features, one dict per track with the reference's keys
+    ('mfccs', 'ssms', 'chromas', 'chroma_med', 'label').  A clique is one smooth latent walk; a cover
+    is the walk linearly time-warped plus noise, its chroma blocks rolled by a random number of bins
+    (exercises the blocked OTI).  Row counts ~ U{(1-j) n_blocks .. (1+j) n_blocks}.  dtype float32 is
+    what the reference stores; float64 features exercise the same arithmetic without input rounding."""
+    dims = dict(EF_DIMS if dims is None else dims)
+    if dims["chromas"] % 12:
+        raise ValueError("chroma block dimension must be a multiple of 12")
+    rng = np.random.default_rng(seed)
+    L = 8
+    proj = {k: rng.normal(0.0, 1.0, size=(L, d)) / np.sqrt(L) for k, d in dims.items()}
+    lo, hi = max(8, int(round((1 - jitter) * n_blocks))), int(round((1 + jitter) * n_blocks))
+    feats = []
+    for cid, size in enumerate(cliques):
+        nb = int(rng.integers(lo, hi + 1))
+        z = np.cumsum(rng.normal(0.0, 0.35, size=(nb, L)), axis=0)
+        z -= z.mean(0)
+        for _ in range(size):
+            n = int(rng.integers(lo, hi + 1))
+            pos = np.linspace(0, nb - 1, n)
+            i0 = np.floor(pos).astype(np.int64)
+            i1 = np.minimum(i0 + 1, nb - 1)
+            w = (pos - i0)[:, None]
+            zz = z[i0] * (1 - w) + z[i1] * w if size > 1 else z[np.minimum(np.arange(n), nb - 1)]
+            f = {}
+            for k in ("mfccs", "ssms"):
+                f[k] = (np.tanh(zz @ proj[k]) + rng.normal(0.0, 0.25, size=(n, dims[k]))).astype(dtype)
+            c = np.abs(np.tanh(zz @ proj["chromas"])) + 0.2 * rng.random((n, dims["chromas"]))
+            shift = int(rng.integers(0, 12)) if size > 1 else 0
+            c = np.roll(c.reshape(n, -1, 12), shift, axis=2).reshape(n, -1).astype(dtype)
+            f["chromas"] = c
+            f["chroma_med"] = np.median(c.reshape(-1, 12), axis=0)
+            f["label"] = "w%d" % cid
+            feats.append(f)
+    return feats

@@ -12,13 +12,19 @@ Reference sources followed (file:line under /root/reference):
   acoss/algorithms/utils/cross_recurrence.py:106-134  get_csm_blocked_oti
   acoss/algorithms/utils/cross_recurrence.py:137-161  csm_to_binary
   acoss/algorithms/utils/alignment_tools.py:8-46      delta_func / match / smith_waterman_constrained
+  acoss/algorithms/utils/similarity_fusion.py:38-54   getWCSM
+  acoss/algorithms/earlyfusion_traile.py:157-198      EarlyFusion.similarity (the four scores of one pair)
+The last two are pinned by ``tests/golden/make_golden_earlyfusion_full.py`` ->
+``tests/golden/earlyfusion_full_golden.npz`` (the reference's own ``EarlyFusion.similarity`` method executed
+on seeded block features).
 """
 from __future__ import annotations
 
 import numpy as np
 
 __all__ = ["get_oti", "get_csm", "get_csm_cosine", "get_csm_blocked_oti", "csm_to_binary",
-           "nneighbs", "smith_waterman_constrained", "smith_waterman_constrained_x10"]
+           "nneighbs", "smith_waterman_constrained", "smith_waterman_constrained_x10",
+           "get_wcsm", "early_fusion_csm", "similarity_pair"]
 
 
 def get_oti(C1, C2) -> int:
@@ -138,3 +144,44 @@ def smith_waterman_constrained_x10(B) -> int:
         S[i, 3:] = row
         best = max(best, int(row.max()))
     return best
+
+
+def get_wcsm(CSMAB, k1, k2, Mu=0.5):
+    """Exponentially weighted cross-similarity of a cross-dissimilarity matrix
+    (similarity_fusion.py:38-54): Eps = (mean of the k2 smallest of the row + mean of the k1 smallest
+    of the column + d) / 3, W = exp(-d^2 / (2 (Mu Eps)^2)).  np.partition raises ValueError when
+    k2 >= columns or k1 >= rows, as the reference does."""
+    CSMAB = np.asarray(CSMAB)
+    m1 = np.mean(np.partition(CSMAB, k2, 1)[:, 0:k2], 1)
+    m2 = np.mean(np.partition(CSMAB, k1, 0)[0:k1, :], 0)
+    Eps = m1[:, None] + m2[None, :] + CSMAB
+    Eps /= 3
+    return np.exp(-CSMAB ** 2 / (2 * (Mu * Eps) ** 2))
+
+
+def early_fusion_csm(csms, K):
+    """exp(-(sum of getWCSM(C, K, K) over the CSMs, in the order given)) — the "distance" matrix the
+    early score binarises (earlyfusion_traile.py:178-183)."""
+    total = np.zeros_like(csms[0])
+    for C in csms:
+        total += get_wcsm(C, K, K)
+    return np.exp(-total)
+
+
+def similarity_pair(f1, f2, kappa=0.1, K=10, want_matrices=False):
+    """The four scores EarlyFusion.similarity stores for one pair (earlyfusion_traile.py:166-183):
+    'mfccs' / 'ssms' Euclidean CSMs, 'chromas' blocked-OTI cosine CSM, 'early' = SW of the binarised
+    exp(-sum of the three WCSMs).  f1 / f2: block-feature dictionaries of load_features."""
+    csms = {
+        "mfccs": get_csm(f1["mfccs"], f2["mfccs"]),
+        "ssms": get_csm(f1["ssms"], f2["ssms"]),
+        "chromas": get_csm_blocked_oti(f1["chromas"], f2["chromas"], f1["chroma_med"], f2["chroma_med"],
+                                       get_csm_cosine),
+    }
+    mats = dict(csms)
+    mats["early"] = early_fusion_csm([csms["mfccs"], csms["ssms"], csms["chromas"]], K)
+    bins = {s: csm_to_binary(mats[s], kappa) for s in mats}
+    scores = {s: smith_waterman_constrained(bins[s]) for s in mats}
+    if want_matrices:
+        return scores, mats, bins
+    return scores
