@@ -55,7 +55,14 @@ struct acoss_ctx {
     size_t ev_used = 0;
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    double stage_ms[4] = {0, 0, 0, 0};
+    double stage_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0..3] Serra09 pipeline, [4..8] EarlyFusion pipeline
+    // EarlyFusion block features (acoss_ef_set_tracks): float64, row pitch ef_dp[k], kinds mfccs / ssms / chromas
+    Buf ef_feat[3], ef_sq[2], ef_cmed, ef_off;
+    std::vector<int64_t> ef_hoff;
+    int32_t ef_d[3] = {0, 0, 0}, ef_dp[3] = {0, 0, 0};
+    int32_t ef_tracks = 0;
+    Buf ef_csm, ef_stat, ef_shapes, ef_nn, ef_csmoff, ef_oti, ef_pairs, ef_scores, ef_bits, ef_bitoff;
+    int64_t ef_stats[4] = {0, 0, 0, 0};
 };
 
 static cudaEvent_t get_event(acoss_ctx *c) {
@@ -156,7 +163,10 @@ int acoss_destroy(acoss_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Buf *bufs[] = {&c->pairs, &c->scores, &c->oti, &c->status, &c->crp, &c->rows, &c->cols, &c->thr_q, &c->thr_r,
-                   &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap, &c->dbg};
+                   &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap, &c->dbg,
+                   &c->ef_feat[0], &c->ef_feat[1], &c->ef_feat[2], &c->ef_sq[0], &c->ef_sq[1], &c->ef_cmed, &c->ef_off,
+                   &c->ef_csm, &c->ef_stat, &c->ef_shapes, &c->ef_nn, &c->ef_csmoff, &c->ef_oti, &c->ef_pairs,
+                   &c->ef_scores, &c->ef_bits, &c->ef_bitoff};
     for (Buf *b : bufs) free_buf(*b);
     if (c->own_frames && c->d_frames) cudaFree(c->d_frames);
     if (c->d_offsets) cudaFree(c->d_offsets);
@@ -700,6 +710,218 @@ int acoss_stage_ms(acoss_ctx *c, double ms[4]) {
 int acoss_last_stats(acoss_ctx *c, int64_t stats[8]) {
     if (!c || !stats) { acoss_set_error("last_stats: NULL argument"); return ACOSS_E_INVALID; }
     memcpy(stats, c->stats, sizeof(c->stats));
+    return ACOSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// EarlyFusion pair scoring (k5_earlyfusion.cu + k4_knn.cu + k3_dp.cu)
+// ---------------------------------------------------------------------------------------------
+int acoss_ef_set_tracks(acoss_ctx *c, const void *mfccs, int32_t d_mfccs, const void *ssms, int32_t d_ssms,
+                        const void *chromas, int32_t d_chromas, const double *chroma_med, const int64_t *offsets,
+                        int32_t n_tracks, int32_t elem_size) {
+    if (!c || !mfccs || !ssms || !chromas || !chroma_med || !offsets || n_tracks <= 0) { acoss_set_error("ef_set_tracks: bad arguments"); return ACOSS_E_INVALID; }
+    if (elem_size != 4 && elem_size != 8) { acoss_set_error("ef_set_tracks: elem_size must be 4 (float32) or 8 (float64)"); return ACOSS_E_INVALID; }
+    if (d_mfccs <= 0 || d_ssms <= 0 || d_chromas <= 0 || d_chromas % NBINS) { acoss_set_error("ef_set_tracks: feature dimensions must be positive, chroma blocks a multiple of 12"); return ACOSS_E_INVALID; }
+    if (offsets[0] != 0) { acoss_set_error("ef_set_tracks: offsets must start at 0"); return ACOSS_E_INVALID; }
+    for (int t = 0; t < n_tracks; ++t) {
+        const int64_t n = offsets[t + 1] - offsets[t];
+        if (n <= 0 || n > 65535) { acoss_set_error("ef_set_tracks: track %d has %lld blocks (1..65535 supported)", t, (long long)n); return ACOSS_E_INVALID; }
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    c->ef_tracks = 0;
+    const int64_t rows = offsets[n_tracks];
+    const void *src[3] = {mfccs, ssms, chromas};
+    const int32_t d[3] = {d_mfccs, d_ssms, d_chromas};
+    Buf stage;
+    for (int k = 0; k < 3; ++k) {
+        const int dp = (d[k] + 15) / 16 * 16;
+        int rc = ensure(c->ef_feat[k], (size_t)rows * dp * 8);
+        if (rc == ACOSS_OK) rc = ensure(stage, (size_t)rows * d[k] * elem_size);
+        if (rc == ACOSS_OK && k < 2) rc = ensure(c->ef_sq[k], (size_t)rows * 8);
+        if (rc != ACOSS_OK) { free_buf(stage); return rc; }
+        cudaError_t e = cudaMemcpyAsync(stage.p, src[k], (size_t)rows * d[k] * elem_size, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { free_buf(stage); acoss_set_error("ef_set_tracks: H2D copy failed: %s", cudaGetErrorString(e)); return ACOSS_E_CUDA; }
+        rc = launch_ef_widen(stage.p, elem_size, rows, d[k], dp, (double *)c->ef_feat[k].p, st);
+        if (rc == ACOSS_OK) rc = launch_ef_rownorm((double *)c->ef_feat[k].p, rows, dp, k == 2 ? 1 : 0, k < 2 ? (double *)c->ef_sq[k].p : nullptr, st);
+        if (rc != ACOSS_OK) { free_buf(stage); return rc; }
+        e = cudaStreamSynchronize(st);                  // the staging buffer is reused by the next kind
+        if (e != cudaSuccess) { free_buf(stage); acoss_set_error("ef_set_tracks: %s", cudaGetErrorString(e)); return ACOSS_E_CUDA; }
+        c->ef_d[k] = d[k];
+        c->ef_dp[k] = dp;
+    }
+    free_buf(stage);
+    TRY(ensure(c->ef_cmed, (size_t)n_tracks * NBINS * 8));
+    TRY(ensure(c->ef_off, (size_t)(n_tracks + 1) * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->ef_cmed.p, chroma_med, (size_t)n_tracks * NBINS * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->ef_off.p, offsets, (size_t)(n_tracks + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    c->ef_hoff.assign(offsets, offsets + n_tracks + 1);
+    c->ef_tracks = n_tracks;
+    return ACOSS_OK;
+}
+
+// One chunk of n pairs (device pair list d_pairs) -> four device score arrays sc[kind][0..n).
+// bits_dev / bit_off (optional): bit-packed binary matrices of every kind, kind-major; csm stays in c->ef_csm.
+static int ef_run_chunk(acoss_ctx *c, const int32_t *d_pairs, int n, int max_r, int max_c, double kappa, int K,
+                        float *const sc[4], uint32_t *bits_dev, const int64_t *bit_off_dev, int64_t bits_per_kind,
+                        int32_t *oti_dev) {
+    cudaStream_t st = c->stream;
+    const int64_t slot_elems = (int64_t)max_r * max_c;
+    const int64_t kind_stride = slot_elems * n;
+    const int words = (max_c + 31) / 32 + 1;
+    const int64_t slot_words = (int64_t)max_r * words;
+    const int stat_pitch = max_r + max_c;
+    TRY(ensure(c->ef_csm, (size_t)kind_stride * 4 * 8));
+    TRY(ensure(c->ef_stat, (size_t)stat_pitch * n * 3 * 8));
+    TRY(ensure(c->ef_shapes, (size_t)n * 8)); TRY(ensure(c->ef_nn, (size_t)n * 4)); TRY(ensure(c->ef_csmoff, (size_t)n * 8));
+    TRY(ensure(c->ef_oti, (size_t)n * 4));
+    TRY(ensure(c->crp, (size_t)n * slot_words * 4));
+    TRY(ensure(c->rows, (size_t)n * 4)); TRY(ensure(c->cols, (size_t)n * 4));
+    TRY(ensure(c->halo, (size_t)n * 2 * max_r * 16));
+    double *csm = (double *)c->ef_csm.p;
+    const int64_t *off = (const int64_t *)c->ef_off.p;
+    int32_t *oti = oti_dev ? oti_dev : (int32_t *)c->ef_oti.p;
+    TRY(launch_ef_geom(off, d_pairs, n, kappa, slot_elems, (int32_t *)c->ef_shapes.p, (int32_t *)c->ef_nn.p,
+                       (int64_t *)c->ef_csmoff.p, st));
+    TRY(launch_ef_oti((const double *)c->ef_cmed.p, d_pairs, n, oti, st));
+    c->ef_stats[2] += 2;
+    {
+        StageTimer t(c, 4);
+        for (int k = 0; k < 3; ++k) {
+            TRY(launch_ef_csm(k == 2 ? 1 : 0, (const double *)c->ef_feat[k].p, c->ef_dp[k], c->ef_d[k],
+                              k < 2 ? (const double *)c->ef_sq[k].p : nullptr, off, d_pairs, oti, n, max_r, max_c,
+                              csm + k * kind_stride, slot_elems, st));
+            ++c->ef_stats[2];
+        }
+        t.stop();
+    }
+    {
+        StageTimer t(c, 7);
+        TRY(launch_ef_linestat(csm, kind_stride, slot_elems, off, d_pairs, n, max_r, max_c, K, (double *)c->ef_stat.p,
+                               (int64_t)stat_pitch * n, stat_pitch, st));
+        t.stop();
+    }
+    {
+        StageTimer t(c, 8);
+        TRY(launch_ef_fuse(csm, kind_stride, slot_elems, off, d_pairs, n, max_r, max_c, (const double *)c->ef_stat.p,
+                           (int64_t)stat_pitch * n, stat_pitch, csm + 3 * kind_stride, st));
+        t.stop();
+    }
+    c->ef_stats[2] += 2;
+    for (int k = 0; k < 4; ++k) {
+        {
+            StageTimer t(c, 5);
+            CUDA_TRY(cudaMemsetAsync(c->crp.p, 0, (size_t)n * slot_words * 4, st));
+            TRY(launch_knn_rows(csm + k * kind_stride, (const int64_t *)c->ef_csmoff.p, (const int32_t *)c->ef_shapes.p,
+                                (const int32_t *)c->ef_nn.p, n, max_r, max_c, (uint32_t *)c->crp.p, slot_words, words,
+                                bits_dev ? bits_dev + k * bits_per_kind : nullptr, bit_off_dev, (int32_t *)c->rows.p,
+                                (int32_t *)c->cols.p, st));
+            t.stop();
+        }
+        {
+            StageTimer t(c, 6);
+            int64_t launches = 0;
+            TRY(launch_dp_bits((const uint32_t *)c->crp.p, slot_words, words, (const int32_t *)c->rows.p,
+                               (const int32_t *)c->cols.p, n, max_c, ACOSS_ALIGN_SW, 0.5f, 0.5f, sc[k],
+                               (uint32_t *)c->halo.p, max_r, st, &launches));
+            t.stop();
+        }
+        c->ef_stats[2] += 2;
+    }
+    return ACOSS_OK;
+}
+
+static int ef_check_pairs(acoss_ctx *c, const int32_t *pairs, int64_t n, double kappa, int K, int *max_r, int *max_c,
+                          int64_t *cells) {
+    if (c->ef_tracks <= 0) { acoss_set_error("EarlyFusion features are not loaded: call acoss_ef_set_tracks first"); return ACOSS_E_INVALID; }
+    if (!(kappa >= 0.0)) { acoss_set_error("kappa must be >= 0"); return ACOSS_E_INVALID; }
+    if (K < 1 || K > ef_linestat_max_k()) { acoss_set_error("K must be in 1..%d", ef_linestat_max_k()); return ACOSS_E_INVALID; }
+    int mr = 1, mc = 1;
+    int64_t cl = 0;
+    for (int64_t k = 0; k < n; ++k) {
+        const int q = pairs[2 * k], r = pairs[2 * k + 1];
+        if (q < 0 || r < 0 || q >= c->ef_tracks || r >= c->ef_tracks) { acoss_set_error("pair %lld: track index out of range", (long long)k); return ACOSS_E_INVALID; }
+        const int M = (int)(c->ef_hoff[q + 1] - c->ef_hoff[q]), N = (int)(c->ef_hoff[r + 1] - c->ef_hoff[r]);
+        // np.partition(CSM, K, axis) raises ValueError when K is not a valid index (similarity_fusion.py:48-51)
+        if (K >= M || K >= N) { acoss_set_error("pair %lld: K = %d needs more than K blocks per track (%d x %d); the reference raises ValueError", (long long)k, K, M, N); return ACOSS_E_INVALID; }
+        if (kappa >= 1.0 && (int)kappa > N) { acoss_set_error("pair %lld: kappa = %d neighbours > %d columns (np.argpartition would raise)", (long long)k, (int)kappa, N); return ACOSS_E_INVALID; }
+        mr = std::max(mr, M); mc = std::max(mc, N);
+        cl += (int64_t)M * N;
+    }
+    if (mc > 200 * 1024 / 8) { acoss_set_error("tracks longer than %d blocks are not supported by the k-NN kernel", 200 * 1024 / 8); return ACOSS_E_INVALID; }
+    *max_r = mr; *max_c = mc; *cells = cl;
+    return ACOSS_OK;
+}
+
+int acoss_ef_score_pairs(acoss_ctx *c, const int32_t *pairs, int64_t n_pairs, double kappa, int32_t K, float *scores) {
+    if (!c || (n_pairs > 0 && (!pairs || !scores)) || n_pairs < 0) { acoss_set_error("ef_score_pairs: bad arguments"); return ACOSS_E_INVALID; }
+    if (n_pairs == 0) return ACOSS_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int max_r, max_c;
+    int64_t cells;
+    TRY(ef_check_pairs(c, pairs, n_pairs, kappa, K, &max_r, &max_c, &cells));
+    cudaStream_t st = c->stream;
+    TRY(ensure(c->ef_pairs, (size_t)n_pairs * 8));
+    TRY(ensure(c->ef_scores, (size_t)n_pairs * 4 * 4));
+    CUDA_TRY(cudaMemcpyAsync(c->ef_pairs.p, pairs, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
+    // slots per chunk from the workspace limit: 4 float64 matrices + the bit-packed copy + line statistics per slot
+    const int words = (max_c + 31) / 32 + 1;
+    const int64_t per_slot = (int64_t)max_r * max_c * 8 * 4 + (int64_t)max_r * words * 4 + (int64_t)(max_r + max_c) * 24 + 2 * (int64_t)max_r * 16 + 64;
+    int64_t slots = std::max<int64_t>(1, std::min<int64_t>(c->ws_limit / per_slot, 32768));
+    slots = std::min<int64_t>(slots, n_pairs);
+    c->ef_stats[0] = n_pairs; c->ef_stats[1] = cells; c->ef_stats[2] = 0; c->ef_stats[3] = 0;
+    float *dsc = (float *)c->ef_scores.p;
+    for (int64_t first = 0; first < n_pairs; first += slots) {
+        const int n = (int)std::min<int64_t>(slots, n_pairs - first);
+        float *const sc[4] = {dsc + first, dsc + n_pairs + first, dsc + 2 * n_pairs + first, dsc + 3 * n_pairs + first};
+        TRY(ef_run_chunk(c, (const int32_t *)c->ef_pairs.p + 2 * first, n, max_r, max_c, kappa, K, sc, nullptr, nullptr, 0, nullptr));
+        ++c->ef_stats[3];
+    }
+    CUDA_TRY(cudaMemcpyAsync(scores, dsc, (size_t)n_pairs * 4 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ACOSS_OK;
+}
+
+int acoss_ef_dump_pair(acoss_ctx *c, int32_t q, int32_t r, double kappa, int32_t K, int32_t *oti, double *csms,
+                       uint32_t *bits, float *scores) {
+    if (!c) { acoss_set_error("NULL context"); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int32_t pr[2] = {q, r};
+    int max_r, max_c;
+    int64_t cells;
+    TRY(ef_check_pairs(c, pr, 1, kappa, K, &max_r, &max_c, &cells));
+    cudaStream_t st = c->stream;
+    const int64_t wpm = (int64_t)max_r * ((max_c + 31) / 32);
+    TRY(ensure(c->ef_pairs, 8)); TRY(ensure(c->ef_scores, 16)); TRY(ensure(c->ef_bits, (size_t)wpm * 4 * 4)); TRY(ensure(c->ef_bitoff, 8));
+    TRY(ensure(c->ef_oti, 4));
+    CUDA_TRY(cudaMemcpyAsync(c->ef_pairs.p, pr, 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(c->ef_bitoff.p, 0, 8, st));
+    float *dsc = (float *)c->ef_scores.p;
+    float *const sc[4] = {dsc, dsc + 1, dsc + 2, dsc + 3};
+    TRY(ef_run_chunk(c, (const int32_t *)c->ef_pairs.p, 1, max_r, max_c, kappa, K, sc, (uint32_t *)c->ef_bits.p,
+                     (const int64_t *)c->ef_bitoff.p, wpm, nullptr));
+    if (oti) CUDA_TRY(cudaMemcpyAsync(oti, c->ef_oti.p, 4, cudaMemcpyDeviceToHost, st));
+    if (csms) CUDA_TRY(cudaMemcpyAsync(csms, c->ef_csm.p, (size_t)cells * 4 * 8, cudaMemcpyDeviceToHost, st));
+    if (bits) CUDA_TRY(cudaMemcpyAsync(bits, c->ef_bits.p, (size_t)wpm * 4 * 4, cudaMemcpyDeviceToHost, st));
+    if (scores) CUDA_TRY(cudaMemcpyAsync(scores, dsc, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ACOSS_OK;
+}
+
+int acoss_ef_stage_ms(acoss_ctx *c, double ms[5]) {
+    if (!c || !ms) { acoss_set_error("ef_stage_ms: NULL argument"); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fold_spans(c);
+    for (int i = 0; i < 5; ++i) ms[i] = c->stage_ms[4 + i];
+    return ACOSS_OK;
+}
+
+int acoss_ef_last_stats(acoss_ctx *c, int64_t stats[4]) {
+    if (!c || !stats) { acoss_set_error("ef_last_stats: NULL argument"); return ACOSS_E_INVALID; }
+    memcpy(stats, c->ef_stats, sizeof(c->ef_stats));
     return ACOSS_OK;
 }
 

@@ -101,3 +101,20 @@ int launch_pack_bytes(const uint8_t *mats, const int64_t *offsets, const int32_t
 int launch_knn_rows(const double *csms, const int64_t *offsets, const int32_t *shapes, const int32_t *nn, int n,
                     int max_rows, int max_cols, uint32_t *bits_dp, int64_t slot_words, int wpr, uint32_t *bits_out,
                     const int64_t *out_offsets, int32_t *rows, int32_t *cols, cudaStream_t st);
+
+// EarlyFusion stages (k5_earlyfusion.cu)
+int launch_ef_widen(const void *src, int elem_size, int64_t rows, int d, int dp, double *dst, cudaStream_t st);
+int launch_ef_rownorm(double *feat, int64_t rows, int dp, int mode, double *sq, cudaStream_t st);
+int launch_ef_oti(const double *cmed, const int32_t *pairs, int n, int32_t *oti, cudaStream_t st);
+int launch_ef_geom(const int64_t *offsets, const int32_t *pairs, int n, double kappa, int64_t slot_elems,
+                   int32_t *shapes, int32_t *nn, int64_t *csm_off, cudaStream_t st);
+int launch_ef_csm(int mode, const double *feat, int dp, int d, const double *sq, const int64_t *offsets,
+                  const int32_t *pairs, const int32_t *oti, int n, int max_rows, int max_cols, double *csm,
+                  int64_t slot_elems, cudaStream_t st);
+int ef_linestat_max_k();
+int launch_ef_linestat(const double *csm, int64_t kind_stride, int64_t slot_elems, const int64_t *offsets,
+                       const int32_t *pairs, int n, int max_rows, int max_cols, int K, double *stat,
+                       int64_t stat_kind_stride, int stat_pitch, cudaStream_t st);
+int launch_ef_fuse(const double *csm, int64_t kind_stride, int64_t slot_elems, const int64_t *offsets,
+                   const int32_t *pairs, int n, int max_rows, int max_cols, const double *stat,
+                   int64_t stat_kind_stride, int stat_pitch, double *out, cudaStream_t st);

@@ -1,18 +1,24 @@
-"""``EarlyFusion`` flavour of the shared binarise + Smith-Waterman path (reference:
-/root/reference/acoss/algorithms/earlyfusion_traile.py:157-198 and the in-tree numba kernels it
-calls, utils/cross_recurrence.py + utils/alignment_tools.py).
+"""Drop-in ``EarlyFusion`` plugin (reference: /root/reference/acoss/algorithms/earlyfusion_traile.py:20-198
+and the in-tree kernels it calls, utils/cross_recurrence.py, utils/similarity_fusion.py:38-54,
+utils/alignment_tools.py).
 
-In scope this round (BASELINE.json configs[1]): every
-``smith_waterman_constrained(csm_to_binary(CSM, kappa))`` call of ``EarlyFusion.similarity`` runs as
-one batched GPU call (row k-NN select + packed-DPX Smith-Waterman), and the chroma score — OTI of
-the block medians, rolled blocks, cosine CSM — is a complete drop-in.  Out of scope (SURVEY §8f
-rank 4): the beat-synchronous block-feature on-ramp (madmom / skimage) and the SNF "early" fusion;
-``similarity`` therefore consumes precomputed block features exactly as ``load_features`` of the
-reference returns them (keys 'mfccs', 'ssms', 'chromas', 'chroma_med'), and only fills the score
-types it is given CSM recipes for.  The float64 CSMs themselves (get_csm / get_csm_cosine: one BLAS
-GEMM per pair, SURVEY §8a row a8 "fast; not the bottleneck") stay on the host in numpy exactly as
-in the reference plugin; what moves to the GPU is the part the reference spends its time in,
-binarisation + Smith-Waterman (≈15 MCUPS/core in numba).
+``similarity(idxs)`` scores a whole batch of pairs in ONE GPU call (``acoss_ef_score_pairs``): per pair the
+Euclidean cross-similarity matrices of the mfcc and ssm blocks, the blocked-OTI cosine matrix of the chroma
+blocks, the "early" fusion exp(-sum of getWCSM(CSM, K, K)), and
+``smith_waterman_constrained(csm_to_binary(., kappa))`` of all four — ``Ds['mfccs' | 'ssms' | 'chromas' |
+'early'][i, j]`` exactly as earlyfusion_traile.py:166-198 fills them.  The block features of every track are
+uploaded once (``acoss_ef_set_tracks``) and stay resident in HBM; no matrix crosses PCIe.
+
+Out of scope (SURVEY.md §8f rank 4 covers the pair scoring only): the beat-synchronous block-feature
+on-ramp of ``load_features`` (madmom onsets, skimage resize — absent from this image).  ``load_features``
+therefore returns precomputed block features exactly as the reference's returns them (keys 'mfccs', 'ssms',
+'chromas', 'chroma_med', 'label'), from memory or from the reference's own cache file layout.
+``do_late_fusion`` (N x N similarity-network fusion of finished score matrices) is delegated to the
+reference's function when the ``acoss`` package is importable.
+
+``sw_of_csms`` scores caller-supplied float64 cross-similarity matrices (``acoss_knn_sw``); ``get_oti`` /
+``csm_euclidean`` / ``csm_cosine`` / ``csm_blocked_oti`` are small host utilities with the reference's
+semantics for callers that need a single matrix — the plugin itself does not use them.
 """
 from __future__ import annotations
 
@@ -102,9 +108,9 @@ def csm_blocked_oti(X, Y, C1, C2, csm_fn=csm_cosine):
 
 
 class EarlyFusion(CoverAlgorithm):
-    """Constructor signature of the reference class (earlyfusion_traile.py:44-58) plus ``device``
-    and ``features``.  Score types filled: 'mfccs', 'ssms', 'chromas' (the three
-    binarise+Smith-Waterman scores of earlyfusion_traile.py:167-175)."""
+    """Constructor signature of the reference class (earlyfusion_traile.py:44-58) plus ``device``,
+    ``features`` (in-memory block features) and ``cachedir``.  Score types: 'mfccs', 'ssms', 'chromas',
+    'early' (earlyfusion_traile.py:58)."""
 
     def __init__(self, dataset_csv, datapath, chroma_type='hpcp', shortname='benchmark', blocksize=20,
                  mfccs_per_block=50, ssm_res=50, chromas_per_block=40, kappa=0.1, K=10, niters=5,
@@ -118,18 +124,22 @@ class EarlyFusion(CoverAlgorithm):
         self.K = K
         self.niters = niters
         self.log_times = log_times
+        if log_times:
+            self.times = {'features': [], 'raw': []}
         self.device = device
         self.all_block_feats = {}
         self._engine = engine
+        self._resident = False
         CoverAlgorithm.__init__(self, dataset_csv, name="EarlyFusionTraile", datapath=datapath,
                                 shortname=shortname, cachedir=cachedir,
-                                similarity_types=["mfccs", "ssms", "chromas"], features=features)
+                                similarity_types=["mfccs", "ssms", "chromas", "early"], features=features)
 
     def get_cacheprefix(self):
         return "%s/%s_%s_%s" % (self.cachedir, self.name, self.shortname, self.chroma_type)
 
     def load_features(self, i):
-        """Precomputed block features of song i (what the reference's load_features returns)."""
+        """Precomputed block features of song i (what the reference's load_features returns,
+        earlyfusion_traile.py:66-155); records the clique as a side effect."""
         if i not in self.all_block_feats:
             self.all_block_feats[i] = CoverAlgorithm.load_features(self, i)
         return self.all_block_feats[i]
@@ -139,23 +149,44 @@ class EarlyFusion(CoverAlgorithm):
             self._engine = Engine(self.device)
         return self._engine
 
+    def _ensure_resident(self):
+        """Upload every track's block features once (the per-process cache all_block_feats of the
+        reference becomes the HBM-resident feature set)."""
+        if not self._resident:
+            self.engine().ef_set_tracks([self.load_features(i) for i in range(self.N)])
+            self._resident = True
+
     def similarity(self, idxs):
+        """Ds[s][i, j] for s in mfccs / ssms / chromas / early and every (i, j) row of idxs
+        (earlyfusion_traile.py:157-198), one batched GPU call."""
+        import time
         idxs = np.asarray(idxs).reshape(-1, 2)
-        csms = {"mfccs": [], "ssms": [], "chromas": []}
-        for i, j in idxs:
-            f1, f2 = self.load_features(i), self.load_features(j)
-            if "mfccs" in f1:
-                csms["mfccs"].append(csm_euclidean(f1["mfccs"], f2["mfccs"]))
-            if "ssms" in f1:
-                csms["ssms"].append(csm_euclidean(f1["ssms"], f2["ssms"]))
-            if "chromas" in f1:
-                csms["chromas"].append(csm_blocked_oti(f1["chromas"], f2["chromas"], f1["chroma_med"],
-                                                       f2["chroma_med"], csm_cosine))
-        for s, mats in csms.items():
-            if len(mats) == len(idxs) and len(mats):
-                self.Ds[s][idxs[:, 0], idxs[:, 1]] = sw_of_csms(self.engine(), mats, self.kappa)
+        if len(idxs) == 0:
+            return
+        self._ensure_resident()
+        tic = time.time()
+        scores = self.engine().ef_score_pairs(idxs.astype(np.int32), self.kappa, self.K)
+        if self.log_times:
+            self.times['raw'].append((time.time() - tic) / len(idxs))
+        for k, s in enumerate(Engine.EF_KINDS):
+            self.Ds[s][idxs[:, 0], idxs[:, 1]] = scores[k]
+
+    def do_late_fusion(self):
+        """earlyfusion_traile.py:200-206 — SNF of the finished N x N score matrices (post-processing outside
+        the pairwise hot path): the reference's own doSimilarityFusion when importable."""
+        try:
+            from acoss.algorithms.utils.similarity_fusion import doSimilarityFusion
+        except Exception as e:
+            raise NotImplementedError(
+                "do_late_fusion is the reference's N x N similarity-network fusion (similarity_fusion.py), "
+                "outside the pairwise hot path; install the reference package to use it") from e
+        self.Ds["late"] = doSimilarityFusion([1.0 / (1.0 + self.Ds[s]) for s in ["chromas", "ssms", "mfccs"]],
+                                             K=20, niters=20, reg_diag=1)[1]
+        self.Ds["early+late"] = doSimilarityFusion(
+            [1.0 / (1.0 + self.Ds[s]) for s in ["chromas", "ssms", "mfccs", "early"]], K=20, niters=20, reg_diag=1)[1]
 
     def close(self):
         if self._engine is not None:
             self._engine.close()
             self._engine = None
+            self._resident = False

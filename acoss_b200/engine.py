@@ -214,3 +214,68 @@ class Engine:
         check(self._lib.acoss_last_stats(self._ctx, st.ctypes.data))
         return dict(pairs=int(st[0]), fallback_pairs=int(st[1]), launches=int(st[2]), cells=int(st[3]),
                     exact_cells=int(st[4]), status_or=int(st[5]), chunks=int(st[6]))
+
+    # -- EarlyFusion pair scoring ---------------------------------------------------------------
+    EF_KINDS = ("mfccs", "ssms", "chromas", "early")
+
+    def ef_set_tracks(self, feats):
+        """feats: one dict per track with the keys EarlyFusion.load_features returns
+        (earlyfusion_traile.py:66-155): 'mfccs', 'ssms', 'chromas' (n_blocks, d) and 'chroma_med' (12,).
+        float32 features (the reference's dtype) are uploaded as they are; anything else as float64."""
+        n = len(feats)
+        kinds = ("mfccs", "ssms", "chromas")
+        f32 = all(np.asarray(f[k]).dtype == np.float32 for f in feats for k in kinds)
+        dt = np.float32 if f32 else np.float64
+        lens = [int(np.asarray(f["mfccs"]).shape[0]) for f in feats]
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        bufs, dims = [], []
+        for k in kinds:
+            d = int(np.asarray(feats[0][k]).shape[1])
+            for f, ln in zip(feats, lens):
+                a = np.asarray(f[k])
+                if a.ndim != 2 or a.shape != (ln, d):
+                    raise ValueError("'%s' must be (n_blocks, %d) with the same n_blocks for every kind; got %r"
+                                     % (k, d, a.shape))
+            bufs.append(np.ascontiguousarray(np.concatenate([np.asarray(f[k], dtype=dt) for f in feats], axis=0)))
+            dims.append(d)
+        cmed = np.ascontiguousarray(np.stack([np.asarray(f["chroma_med"], dtype=np.float64).reshape(12)
+                                              for f in feats]))
+        check(self._lib.acoss_ef_set_tracks(self._ctx, bufs[0].ctypes.data, dims[0], bufs[1].ctypes.data, dims[1],
+                                            bufs[2].ctypes.data, dims[2], cmed.ctypes.data, offsets.ctypes.data, n,
+                                            4 if f32 else 8))
+        self.ef_offsets = offsets
+        self.ef_h2d_bytes = int(sum(b.nbytes for b in bufs) + cmed.nbytes + offsets.nbytes)
+
+    def ef_score_pairs(self, pairs, kappa: float = 0.1, K: int = 10) -> np.ndarray:
+        """pairs (n, 2) int -> float32 (4, n): rows 'mfccs', 'ssms', 'chromas', 'early' — the four values
+        EarlyFusion.similarity stores per pair (acoss_ef_score_pairs)."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros((4, len(pairs)), dtype=np.float32)
+        check(self._lib.acoss_ef_score_pairs(self._ctx, pairs.ctypes.data, len(pairs), float(kappa), int(K),
+                                             out.ctypes.data))
+        return out
+
+    def ef_dump_pair(self, q: int, r: int, kappa: float = 0.1, K: int = 10) -> dict:
+        """-> dict(oti, csms float64 (4, M, N), bins uint8 (4, M, N), scores float32 (4,)) of one pair."""
+        M = int(self.ef_offsets[q + 1] - self.ef_offsets[q])
+        N = int(self.ef_offsets[r + 1] - self.ef_offsets[r])
+        W = (N + 31) // 32
+        oti = C.c_int32(0)
+        csms = np.zeros((4, M, N), dtype=np.float64)
+        bits = np.zeros((4, M, W), dtype=np.uint32)
+        scores = np.zeros(4, dtype=np.float32)
+        check(self._lib.acoss_ef_dump_pair(self._ctx, int(q), int(r), float(kappa), int(K), C.addressof(oti),
+                                           csms.ctypes.data, bits.ctypes.data, scores.ctypes.data))
+        bins = np.unpackbits(bits.view(np.uint8), axis=2, bitorder="little")[:, :, :N]
+        return dict(oti=int(oti.value), csms=csms, bins=bins, scores=scores)
+
+    def ef_stage_ms(self) -> dict:
+        ms = np.zeros(5, dtype=np.float64)
+        check(self._lib.acoss_ef_stage_ms(self._ctx, ms.ctypes.data))
+        return dict(csm=float(ms[0]), knn=float(ms[1]), sw=float(ms[2]), radii=float(ms[3]), fuse=float(ms[4]))
+
+    def ef_last_stats(self) -> dict:
+        st = np.zeros(4, dtype=np.int64)
+        check(self._lib.acoss_ef_last_stats(self._ctx, st.ctypes.data))
+        return dict(pairs=int(st[0]), cells=int(st[1]), launches=int(st[2]), chunks=int(st[3]))

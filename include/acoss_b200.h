@@ -140,6 +140,41 @@ int acoss_dp_bytes(acoss_ctx *ctx, const uint8_t *mats, const int64_t *offsets, 
 int acoss_knn_sw(acoss_ctx *ctx, const double *csms, const int64_t *offsets, const int32_t *shapes,
                  const int32_t *nn, int64_t n_mats, float *scores, uint32_t *bits_out);
 
+/* ---- EarlyFusion pair scoring (earlyfusion_traile.py:157-198) ------------------------------------------
+ * Replaces the per-process block-feature cache EarlyFusion.all_block_feats / load_features
+ * (earlyfusion_traile.py:66-155): uploads every track's beat-synchronous block features, concatenated over
+ * tracks: mfccs[(offsets[t] + b) * d_mfccs + k] etc., offsets in BLOCKS (n_tracks + 1 entries, all three kinds
+ * have the same number of blocks per track), chroma_med[t * 12 + bin] = the song-level chroma median
+ * (float64).  elem_size: 4 = float32 features (what the reference stores), 8 = float64.  Host memory.  The
+ * device keeps float64 copies (chroma blocks pre-normalised for the cosine CSM) and the squared norms. */
+int acoss_ef_set_tracks(acoss_ctx *ctx, const void *mfccs, int32_t d_mfccs, const void *ssms, int32_t d_ssms,
+                        const void *chromas, int32_t d_chromas, const double *chroma_med, const int64_t *offsets,
+                        int32_t n_tracks, int32_t elem_size);
+
+/* Replaces EarlyFusion.similarity(idxs) (earlyfusion_traile.py:157-198) for a whole batch: per pair
+ * (pairs[2k] = first song i, pairs[2k+1] = second song j) the Euclidean CSMs of the mfcc and ssm blocks
+ * (get_csm, cross_recurrence.py:31-48), the blocked-OTI cosine CSM of the chroma blocks
+ * (get_csm_blocked_oti / get_csm_cosine, :54-134), exp(-sum of getWCSM(CSM, K, K)) (similarity_fusion.py:38-54),
+ * and smith_waterman_constrained(csm_to_binary(., kappa)) of all four.  scores is [4][n_pairs] float32, kind-major:
+ * mfccs, ssms, chromas, early — the values the reference stores in Ds[kind][i][j].  kappa as in
+ * csm_to_binary (0: all ones, < 1: fraction of the columns, else a count); K in 1..64 and smaller than the
+ * block count of every track involved (np.partition raises otherwise: ACOSS_E_INVALID).  Host buffers. */
+int acoss_ef_score_pairs(acoss_ctx *ctx, const int32_t *pairs, int64_t n_pairs, double kappa, int32_t K,
+                         float *scores);
+
+/* Debug dump of one pair (M = blocks of q, N = blocks of r): OTI, the four float64 matrices [4][M * N]
+ * (mfccs, ssms, chromas CSMs and the fused matrix), their binarisations [4][M * ceil(N / 32)] bit-packed, and
+ * the four scores.  Any output pointer may be NULL.  Host buffers. */
+int acoss_ef_dump_pair(acoss_ctx *ctx, int32_t q, int32_t r, double kappa, int32_t K, int32_t *oti, double *csms,
+                       uint32_t *bits, float *scores);
+
+/* Device milliseconds of the EarlyFusion stages since acoss_set_profiling(ctx, 1): [0] CSM contractions,
+ * [1] k-NN binarisation, [2] Smith-Waterman DP, [3] getWCSM row/column radii, [4] fusion (exp) pass. */
+int acoss_ef_stage_ms(acoss_ctx *ctx, double ms[5]);
+/* Counters of the last acoss_ef_score_pairs call: [0] pairs, [1] cells (sum of M * N), [2] kernel launches,
+ * [3] slot chunks. */
+int acoss_ef_last_stats(acoss_ctx *ctx, int64_t stats[4]);
+
 /* Counters of the last acoss_score_pairs* call: [0] pairs, [1] pairs that took the exact
  * fallback, [2] kernel launches, [3] cells (sum of M'*N'), [4] exact re-evaluated candidate cells, [5] OR of the
  * per-pair status words, [6] slot chunks the call was processed in (= launches of each K2 / K3 kernel). */
