@@ -16,6 +16,8 @@
 // GEMMs (K = 480 / 1000 / 1225) but float64 ones: B200 issues DFMA at 64 lanes/clk/SM and has no
 // faster float64 tensor path, so the contraction is a register-tiled DFMA kernel (64x64 CTA tile,
 // 8x4 accumulators per thread, k-major shared-memory tiles read with broadcast LDS.128).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -233,12 +235,152 @@ __global__ void __launch_bounds__(128) ef_csm_kernel(const double *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CSM, second generation.  ncu on the kernel above (profiles/r1_ef_csm.md): the shared-memory pipe is the
+// limiter (l1tex throughput 91 %, FP64 pipe 45 %) — an LDS.128 is served per half-warp, 128 B per wavefront,
+// so the 2 x 16 thread layout pays 4 wavefronts per B fragment.  Here: 64-thread CTAs (2 warps), 8 x 8
+// accumulators per thread, warp = 4 row groups x 8 column groups, tiles kept ROW-major in shared memory
+// ([row][k], pitch 18 doubles) so that one LDS.128 delivers two consecutive k of a row and every half-warp
+// touches exactly 128 distinct bytes (B) or 32 (A): 32 wavefronts per 128 DFMA per warp, half the pipe.
+// Global -> shared goes through cp.async (16 B chunks, two-stage ring), no staging registers.  The k order
+// of every accumulator is unchanged (k ascending, one FMA per k), so the results are bit-identical to the
+// first-generation kernel.
+// ---------------------------------------------------------------------------------------------
+#define EF2_LD 18
+#define EF2_MAXDP 2048   // widest (padded) chroma block the rolled-column map covers
+__device__ __forceinline__ void ef_cp_async16(void *smem, const void *g) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void ef_cp_async8(void *smem, const void *g) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(64) ef_csm2_kernel(const double *__restrict__ feat, int dp, int d,
+                                                     const double *__restrict__ sq,
+                                                     const int64_t *__restrict__ offsets,
+                                                     const int32_t *__restrict__ pairs,
+                                                     const int32_t *__restrict__ oti_a,
+                                                     double *__restrict__ csm, int64_t slot_elems, int tiles_n) {
+    __shared__ __align__(16) double As[2][EF_BM][EF2_LD];
+    __shared__ __align__(16) double Bs[2][EF_BN][EF2_LD];
+    __shared__ short kmap[MODE == 1 ? EF2_MAXDP : 1];
+    const int slot = blockIdx.y;
+    const int q = pairs[2 * slot], r = pairs[2 * slot + 1];
+    const int64_t oq = offsets[q], orr = offsets[r];
+    const int M = (int)(offsets[q + 1] - oq), N = (int)(offsets[r + 1] - orr);
+    const int m0 = (blockIdx.x / tiles_n) * EF_BM, n0 = (blockIdx.x % tiles_n) * EF_BN;
+    if (m0 >= M || n0 >= N) return;
+    const int tid = threadIdx.x;
+    const double *Abase = feat + oq * (int64_t)dp, *Bbase = feat + orr * (int64_t)dp;
+    if (MODE == 1) {                                          // np.roll(X1, oti, axis=2): out[b] = in[(b - oti) mod 12]
+        const int rot = oti_a[slot];
+        for (int k = tid; k < dp; k += 64) {
+            int src = k;
+            if (k < d) {
+                const int t = k / NBINS, b = k - t * NBINS;
+                src = t * NBINS + rot_src(b, rot);
+            }
+            kmap[k] = (short)src;
+        }
+        __syncthreads();
+    }
+    auto issue = [&](int k0, int buf) {
+        const int ch = tid & 7;
+        if (MODE == 1) {
+#pragma unroll 1
+            for (int e = 0; e < 16; ++e) {                    // rolled chroma groups: element-wise gather
+                const int id = tid + 64 * e, row = id >> 4, kk = id & 15;
+                ef_cp_async8(&As[buf][row][kk], Abase + min(m0 + row, M - 1) * dp + (int)kmap[k0 + kk]);
+            }
+        }
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            const int row = (tid >> 3) + 8 * c;
+            if (MODE == 0) ef_cp_async16(&As[buf][row][2 * ch], Abase + min(m0 + row, M - 1) * dp + k0 + 2 * ch);
+            ef_cp_async16(&Bs[buf][row][2 * ch], Bbase + min(n0 + row, N - 1) * dp + k0 + 2 * ch);
+        }
+    };
+    // register tile: rows 32 w + rg + 4 i (i = 0..7), columns cg + 8 j (j = 0..7)
+    const int w = tid >> 5, rg = (tid >> 3) & 3, cg = tid & 7;
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    const int nt = dp / EF_BK;
+    issue(0, 0);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int t = 0; t < nt; ++t) {
+        if (t + 1 < nt) issue((t + 1) * EF_BK, (t + 1) & 1);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();
+        const double *Ap = &As[t & 1][32 * w + rg][0];
+        const double *Bp = &Bs[t & 1][cg][0];
+#pragma unroll
+        for (int k2 = 0; k2 < EF_BK; k2 += 2) {
+            double2 a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double2 *>(Ap + i * 4 * EF2_LD + k2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double2 b = *reinterpret_cast<const double2 *>(Bp + j * 8 * EF2_LD + k2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[i][j] = fma(a[i].x, b.x, acc[i][j]);
+                    acc[i][j] = fma(a[i].y, b.y, acc[i][j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    double *out = csm + (int64_t)slot * slot_elems;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = m0 + 32 * w + rg + 4 * i;
+        if (row >= M) continue;
+        const double sx = (MODE == 0) ? sq[oq + row] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = n0 + cg + 8 * j;
+            if (col >= N) continue;
+            double v;
+            if (MODE == 0) {
+                double c2 = __dsub_rn(__dadd_rn(sx, sq[orr + col]), __dmul_rn(2.0, acc[i][j]));
+                c2 = c2 < 0.0 ? 0.0 : c2;
+                v = sqrt(c2);
+            } else {
+                v = __dsub_rn(1.0, acc[i][j]);
+            }
+            out[(int64_t)row * N + col] = v;
+        }
+    }
+}
+
+static int ef_csm_generation() {
+    static int gen = -1;
+    if (gen < 0) {
+        const char *e = getenv("ACOSS_EF_CSM");               // 1 selects the first-generation kernel (A/B timing)
+        gen = (e && e[0] == '1') ? 1 : 2;
+    }
+    return gen;
+}
+
 int launch_ef_csm(int mode, const double *feat, int dp, int d, const double *sq, const int64_t *offsets,
                   const int32_t *pairs, const int32_t *oti, int n, int max_rows, int max_cols, double *csm,
                   int64_t slot_elems, cudaStream_t st) {
     if (n <= 0) return ACOSS_OK;
     const int tiles_m = (max_rows + EF_BM - 1) / EF_BM, tiles_n = (max_cols + EF_BN - 1) / EF_BN;
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)n);
+    if (ef_csm_generation() == 2 && (mode == 0 || dp <= EF2_MAXDP)) {
+        if (mode == 0) ef_csm2_kernel<0><<<grid, 64, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
+        else ef_csm2_kernel<1><<<grid, 64, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
+        CUDA_TRY(cudaGetLastError());
+        return ACOSS_OK;
+    }
     if (mode == 0) ef_csm_kernel<0><<<grid, 128, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
     else ef_csm_kernel<1><<<grid, 128, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
     CUDA_TRY(cudaGetLastError());
