@@ -257,6 +257,27 @@ __device__ __forceinline__ void ef_cp_async8(void *smem, const void *g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g) : "memory");
 }
 
+// 16 k of one 64 x 64 tile for one thread: acc[i][j] += A[row_i][k] * B[col_j][k], k ascending
+template <bool FULL>
+__device__ __forceinline__ void ef_tile_fma(const double *Ap, const double *Bp, int jmax, double (&acc)[8][8]) {
+#pragma unroll
+    for (int k2 = 0; k2 < EF_BK; k2 += 2) {
+        double2 a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double2 *>(Ap + i * 4 * EF2_LD + k2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (!FULL && j >= jmax) break;                    // warp-uniform
+            const double2 b = *reinterpret_cast<const double2 *>(Bp + j * 8 * EF2_LD + k2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                acc[i][j] = fma(a[i].x, b.x, acc[i][j]);
+                acc[i][j] = fma(a[i].y, b.y, acc[i][j]);
+            }
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(64) ef_csm2_kernel(const double *__restrict__ feat, int dp, int d,
                                                      const double *__restrict__ sq,
@@ -310,6 +331,9 @@ __global__ void __launch_bounds__(64) ef_csm2_kernel(const double *__restrict__ 
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    // ragged edge tiles: a warp whose 32 rows lie past M only helps loading; 8-column groups past N are skipped
+    const bool warp_live = m0 + 32 * w < M;
+    const int jmax = min(8, (N - n0 + 7) >> 3);
     const int nt = dp / EF_BK;
     issue(0, 0);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -320,20 +344,9 @@ __global__ void __launch_bounds__(64) ef_csm2_kernel(const double *__restrict__ 
         __syncthreads();
         const double *Ap = &As[t & 1][32 * w + rg][0];
         const double *Bp = &Bs[t & 1][cg][0];
-#pragma unroll
-        for (int k2 = 0; k2 < EF_BK; k2 += 2) {
-            double2 a[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double2 *>(Ap + i * 4 * EF2_LD + k2);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const double2 b = *reinterpret_cast<const double2 *>(Bp + j * 8 * EF2_LD + k2);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    acc[i][j] = fma(a[i].x, b.x, acc[i][j]);
-                    acc[i][j] = fma(a[i].y, b.y, acc[i][j]);
-                }
-            }
+        if (warp_live) {
+            if (jmax == 8) ef_tile_fma<true>(Ap, Bp, 8, acc);    // interior tile: fully unrolled, fragments prefetched
+            else ef_tile_fma<false>(Ap, Bp, jmax, acc);          // ragged right edge: 8-column groups past N skipped
         }
         __syncthreads();
     }
@@ -360,11 +373,134 @@ __global__ void __launch_bounds__(64) ef_csm2_kernel(const double *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CSM, third generation: the float64 tensor path (DMMA, mma.sync.m8n8k4.f64 — tcgen05 has no float64
+// kind; on sm_100a the legacy warp-level MMA is the only float64 tensor instruction).  ncu on the second
+// generation (profiles/r1_ef_csm.md): FP64 pipe 56 %, two warps per scheduler at 255 registers, stalls are
+// the half-rate DFMA issue itself.  One DMMA replaces 8 DFMA per lane and needs one A and one B double
+// per lane: 64 x 64 CTA tile, 2 x 2 warps of 32 x 32 (4 x 4 MMA tiles, 32 accumulator doubles per lane),
+// 8 LDS.64 per 16 DMMA.  Shared tiles stay row-major [row][k] with a pitch of 20 doubles, so the 4 rows x
+// 4 k a half-warp reads fall in 32 distinct banks.  cp.async two-stage ring as above.
+// ---------------------------------------------------------------------------------------------
+#define EF3_LD 20
+__device__ __forceinline__ void ef_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) ef_csm3_kernel(const double *__restrict__ feat, int dp, int d,
+                                                      const double *__restrict__ sq,
+                                                      const int64_t *__restrict__ offsets,
+                                                      const int32_t *__restrict__ pairs,
+                                                      const int32_t *__restrict__ oti_a,
+                                                      double *__restrict__ csm, int64_t slot_elems, int tiles_n) {
+    __shared__ __align__(16) double As[2][EF_BM][EF3_LD];
+    __shared__ __align__(16) double Bs[2][EF_BN][EF3_LD];
+    __shared__ short kmap[MODE == 1 ? EF2_MAXDP : 1];
+    const int slot = blockIdx.y;
+    const int q = pairs[2 * slot], r = pairs[2 * slot + 1];
+    const int64_t oq = offsets[q], orr = offsets[r];
+    const int M = (int)(offsets[q + 1] - oq), N = (int)(offsets[r + 1] - orr);
+    const int m0 = (blockIdx.x / tiles_n) * EF_BM, n0 = (blockIdx.x % tiles_n) * EF_BN;
+    if (m0 >= M || n0 >= N) return;
+    const int tid = threadIdx.x;
+    const double *Abase = feat + oq * (int64_t)dp, *Bbase = feat + orr * (int64_t)dp;
+    if (MODE == 1) {                                          // np.roll(X1, oti, axis=2): out[b] = in[(b - oti) mod 12]
+        const int rot = oti_a[slot];
+        for (int k = tid; k < dp; k += 128) {
+            int src = k;
+            if (k < d) {
+                const int t = k / NBINS, b = k - t * NBINS;
+                src = t * NBINS + rot_src(b, rot);
+            }
+            kmap[k] = (short)src;
+        }
+        __syncthreads();
+    }
+    auto issue = [&](int k0, int buf) {
+        const int ch = tid & 7;
+        if (MODE == 1) {
+#pragma unroll 1
+            for (int e = 0; e < 8; ++e) {                     // rolled chroma groups: element-wise gather
+                const int id = tid + 128 * e, row = id >> 4, kk = id & 15;
+                ef_cp_async8(&As[buf][row][kk], Abase + min(m0 + row, M - 1) * dp + (int)kmap[k0 + kk]);
+            }
+        }
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            const int row = (tid >> 3) + 16 * c;
+            if (MODE == 0) ef_cp_async16(&As[buf][row][2 * ch], Abase + min(m0 + row, M - 1) * dp + k0 + 2 * ch);
+            ef_cp_async16(&Bs[buf][row][2 * ch], Bbase + min(n0 + row, N - 1) * dp + k0 + 2 * ch);
+        }
+    };
+    // warp (wr, wc) owns rows 32 wr .. +31 and columns 32 wc .. +31; MMA tile (rt, ct) of it: lane holds
+    // C[8 rt + g][8 ct + 2 tg + {0,1}], reads A[8 rt + g][k + tg] and B[k + tg][8 ct + g]  (g = lane / 4, tg = lane % 4)
+    const int lane = tid & 31, wr = (tid >> 5) >> 1, wc = (tid >> 5) & 1, g = lane >> 2, tg = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const bool warp_live = m0 + 32 * wr < M && n0 + 32 * wc < N;      // ragged edge tiles: idle quadrants only load
+    const int nt = dp / EF_BK;
+    issue(0, 0);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int t = 0; t < nt; ++t) {
+        if (t + 1 < nt) issue((t + 1) * EF_BK, (t + 1) & 1);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();
+        if (warp_live) {
+            const double *Ap = &As[t & 1][32 * wr + g][tg];
+            const double *Bp = &Bs[t & 1][32 * wc + g][tg];
+#pragma unroll
+            for (int k4 = 0; k4 < EF_BK; k4 += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = Ap[i * 8 * EF3_LD + k4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = Bp[j * 8 * EF3_LD + k4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ef_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        __syncthreads();
+    }
+    if (!warp_live) return;
+    double *out = csm + (int64_t)slot * slot_elems;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + 32 * wr + 8 * i + g;
+        if (row >= M) continue;
+        const double sx = (MODE == 0) ? sq[oq + row] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = n0 + 32 * wc + 8 * j + 2 * tg + h;
+                if (col >= N) continue;
+                double v;
+                if (MODE == 0) {
+                    double c2 = __dsub_rn(__dadd_rn(sx, sq[orr + col]), __dmul_rn(2.0, acc[i][j][h]));
+                    c2 = c2 < 0.0 ? 0.0 : c2;
+                    v = sqrt(c2);
+                } else {
+                    v = __dsub_rn(1.0, acc[i][j][h]);
+                }
+                out[(int64_t)row * N + col] = v;
+            }
+    }
+}
+
 static int ef_csm_generation() {
     static int gen = -1;
     if (gen < 0) {
-        const char *e = getenv("ACOSS_EF_CSM");               // 1 selects the first-generation kernel (A/B timing)
-        gen = (e && e[0] == '1') ? 1 : 2;
+        const char *e = getenv("ACOSS_EF_CSM");               // 1 / 2 select the DFMA kernels (A/B timing)
+        gen = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3;
     }
     return gen;
 }
@@ -375,7 +511,13 @@ int launch_ef_csm(int mode, const double *feat, int dp, int d, const double *sq,
     if (n <= 0) return ACOSS_OK;
     const int tiles_m = (max_rows + EF_BM - 1) / EF_BM, tiles_n = (max_cols + EF_BN - 1) / EF_BN;
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)n);
-    if (ef_csm_generation() == 2 && (mode == 0 || dp <= EF2_MAXDP)) {
+    if (ef_csm_generation() == 3 && (mode == 0 || dp <= EF2_MAXDP)) {
+        if (mode == 0) ef_csm3_kernel<0><<<grid, 128, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
+        else ef_csm3_kernel<1><<<grid, 128, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
+        CUDA_TRY(cudaGetLastError());
+        return ACOSS_OK;
+    }
+    if (ef_csm_generation() >= 2 && (mode == 0 || dp <= EF2_MAXDP)) {
         if (mode == 0) ef_csm2_kernel<0><<<grid, 64, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
         else ef_csm2_kernel<1><<<grid, 64, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
         CUDA_TRY(cudaGetLastError());
