@@ -140,8 +140,19 @@ __global__ void __launch_bounds__(256) knn_rows_warp_kernel(const double *__rest
         for (int t = 0; t < NT; ++t) alive |= (lane + 32 * t < N) ? (1u << t) : 0u;
         unsigned kk = (unsigned)(nn - 1), alive_cnt = (unsigned)N;
         bool single = false;
+        // bits on which all keys of the row agree (sign, exponent, leading mantissa bits of similar distances)
+        // cannot split the set: only the differing bit positions are visited, most significant first
+        unsigned ah = ~0u, oh = 0u, al = ~0u, ol = 0u;
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            if ((alive >> t) & 1u) { ah &= hi[t]; oh |= hi[t]; al &= lo[t]; ol |= lo[t]; }
+        const unsigned dh = __reduce_and_sync(0xffffffffu, ah) ^ __reduce_or_sync(0xffffffffu, oh);
+        const unsigned dl = __reduce_and_sync(0xffffffffu, al) ^ __reduce_or_sync(0xffffffffu, ol);
         for (int half = 0; half < 2 && !single; ++half) {
-            for (int b = 31; b >= 0; --b) {
+            unsigned todo = half == 0 ? dh : dl;
+            while (todo) {
+                const int b = 31 - __clz(todo);
+                todo &= ~(1u << b);
                 unsigned zero = 0u;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {

@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(128) ef_csm3_kernel(const double *__restrict__
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const bool warp_live = m0 + 32 * wr < M && n0 + 32 * wc < N;      // ragged edge tiles: idle quadrants only load
+    const int imax = min(4, (M - m0 - 32 * wr + 7) >> 3), jmax = min(4, (N - n0 - 32 * wc + 7) >> 3);
     const int nt = dp / EF_BK;
     issue(0, 0);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -455,17 +456,33 @@ __global__ void __launch_bounds__(128) ef_csm3_kernel(const double *__restrict__
         if (warp_live) {
             const double *Ap = &As[t & 1][32 * wr + g][tg];
             const double *Bp = &Bs[t & 1][32 * wc + g][tg];
+            if (imax == 4 && jmax == 4) {                     // interior quadrant
 #pragma unroll
-            for (int k4 = 0; k4 < EF_BK; k4 += 4) {
-                double a[4], b[4];
+                for (int k4 = 0; k4 < EF_BK; k4 += 4) {
+                    double a[4], b[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = Ap[i * 8 * EF3_LD + k4];
+                    for (int i = 0; i < 4; ++i) a[i] = Ap[i * 8 * EF3_LD + k4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Bp[j * 8 * EF3_LD + k4];
+                    for (int j = 0; j < 4; ++j) b[j] = Bp[j * 8 * EF3_LD + k4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ef_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                        for (int j = 0; j < 4; ++j) ef_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+            } else {                                          // ragged edge: 8 x 8 MMA tiles past M / N are skipped
+#pragma unroll
+                for (int k4 = 0; k4 < EF_BK; k4 += 4) {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = Ap[i * 8 * EF3_LD + k4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) b[j] = Bp[j * 8 * EF3_LD + k4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (i < imax && j < jmax) ef_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
             }
         }
         __syncthreads();
@@ -512,6 +529,14 @@ int launch_ef_csm(int mode, const double *feat, int dp, int d, const double *sq,
     const int tiles_m = (max_rows + EF_BM - 1) / EF_BM, tiles_n = (max_cols + EF_BN - 1) / EF_BN;
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)n);
     if (ef_csm_generation() == 3 && (mode == 0 || dp <= EF2_MAXDP)) {
+        static bool carve[16] = {false};                      // 40 KB static tiles per CTA: ask for the full carve-out
+        int dev = 0;                                          // so that 5 CTAs fit an SM
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 16 && !carve[dev]) {
+            cudaFuncSetAttribute(ef_csm3_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(ef_csm3_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            carve[dev] = true;
+        }
         if (mode == 0) ef_csm3_kernel<0><<<grid, 128, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
         else ef_csm3_kernel<1><<<grid, 128, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
         CUDA_TRY(cudaGetLastError());

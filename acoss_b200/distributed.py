@@ -50,32 +50,51 @@ def gather_scores(local_scores, bounds, rank: int, world: int, device=None):
 
 
 def all_pairwise_distributed(alg, symmetric=True, score_fn=None):
-    """Distributed `all_pairwise` for a Serra09-style plugin `alg` (must provide `_pair_array`,
-    `load_features`, `Ds`, `N`, `m`, `tau`).  Every rank calls this; on return every rank's
-    `alg.Ds[key]` holds the full (symmetrised) score matrix.  `score_fn(pairs) -> float32 scores`
-    defaults to the CUDA engine of `alg`."""
+    """Distributed `all_pairwise` for a plugin `alg`.  Every rank calls this; on return every rank's
+    `alg.Ds[key]` holds the full (symmetrised) score matrix of every key.
+
+    Serra09-style plugins (one score per pair; `_pair_array`, `load_features`, `Ds`, `N`, `m`, `tau`) are
+    balanced by DP cells (n_q - m tau)(n_r - m tau).  Plugins with several scores per pair (EarlyFusion:
+    'mfccs', 'ssms', 'chromas', 'early') provide `pair_weights(pairs)` and `score_pairs(pairs) -> float32
+    (n_keys, n)` with rows in `alg.Ds` key order; their score rows travel in ONE gather.
+    `score_fn(pairs)` overrides the scoring call (CPU tests)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     pairs = alg._pair_array(symmetric)
-    lens = np.array([alg.load_features(i).shape[0] for i in range(alg.N)], dtype=np.int64)
-    incr = int(alg.m) * int(alg.tau)
-    cells = (lens[pairs[:, 0]] - incr) * (lens[pairs[:, 1]] - incr)
+    if hasattr(alg, "pair_weights"):
+        cells = np.asarray(alg.pair_weights(pairs), dtype=np.float64)
+    else:
+        lens = np.array([alg.load_features(i).shape[0] for i in range(alg.N)], dtype=np.int64)
+        incr = int(alg.m) * int(alg.tau)
+        cells = (lens[pairs[:, 0]] - incr) * (lens[pairs[:, 1]] - incr)
     bounds = shard_bounds(cells, world)
     mine = pairs[bounds[rank]:bounds[rank + 1]]
-    if score_fn is None:
+    keys = list(alg.Ds.keys())
+    if score_fn is not None:
+        local = np.asarray(score_fn(mine), dtype=np.float32)
+    elif hasattr(alg, "score_pairs"):
+        local = np.asarray(alg.score_pairs(mine), dtype=np.float32)
+    else:
         eng = alg.engine()
         tile = getattr(alg, "tile_pairs", 1 << 16)
         parts = [eng.score_pairs(mine[k:k + tile].astype(np.int32), alg.params()) for k in range(0, len(mine), tile)]
         local = np.concatenate(parts) if parts else np.zeros(0, np.float32)
-    else:
-        local = np.asarray(score_fn(mine), dtype=np.float32)
+    rows = 1 if local.ndim == 1 else local.shape[0]
+    if rows not in (1, len(keys)):
+        raise ValueError("score rows (%d) do not match the score types %r" % (rows, keys))
     backend = dist.get_backend() if dist.is_initialized() else "none"
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    full = gather_scores(torch.from_numpy(local).to(dev), bounds, rank, world).cpu().numpy()
-    for key in alg.Ds.keys():
-        alg.Ds[key][pairs[:, 0], pairs[:, 1]] = full
+    # one gather for all score rows: rank r contributes rows x (bounds[r+1] - bounds[r]) floats, row-major
+    flat = np.ascontiguousarray(local.reshape(rows, -1)).ravel()
+    full = gather_scores(torch.from_numpy(flat).to(dev), bounds * rows, rank, world).cpu().numpy()
+    per_key = np.empty((rows, len(pairs)), dtype=np.float32)
+    for r in range(world):
+        a, b = int(bounds[r]), int(bounds[r + 1])
+        per_key[:, a:b] = full[a * rows:b * rows].reshape(rows, b - a)
+    for k, key in enumerate(keys):
+        alg.Ds[key][pairs[:, 0], pairs[:, 1]] = per_key[k if rows > 1 else 0]
         if symmetric:
             alg.Ds[key] += alg.Ds[key].T
     return bounds

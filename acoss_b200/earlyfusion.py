@@ -171,6 +171,21 @@ class EarlyFusion(CoverAlgorithm):
         for k, s in enumerate(Engine.EF_KINDS):
             self.Ds[s][idxs[:, 0], idxs[:, 1]] = scores[k]
 
+    # -- hooks of acoss_b200.distributed.all_pairwise_distributed (one process per GPU) -----------------
+    def pair_weights(self, pairs):
+        """Work of a pair = cells of its cross-similarity matrices (blocks_i x blocks_j)."""
+        pairs = np.asarray(pairs).reshape(-1, 2)
+        nb = np.array([np.asarray(self.load_features(i)["mfccs"]).shape[0] for i in range(self.N)], dtype=np.int64)
+        return nb[pairs[:, 0]] * nb[pairs[:, 1]]
+
+    def score_pairs(self, pairs):
+        """float32 (4, n): rows in Ds key order (mfccs, ssms, chromas, early)."""
+        pairs = np.asarray(pairs).reshape(-1, 2)
+        if len(pairs) == 0:
+            return np.zeros((4, 0), dtype=np.float32)
+        self._ensure_resident()
+        return self.engine().ef_score_pairs(pairs.astype(np.int32), self.kappa, self.K)
+
     def do_late_fusion(self):
         """earlyfusion_traile.py:200-206 — SNF of the finished N x N score matrices (post-processing outside
         the pairwise hot path): the reference's own doSimilarityFusion when importable."""

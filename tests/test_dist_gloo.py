@@ -38,6 +38,58 @@ def _worker(rank, world, port, tmp, q):
     dist.destroy_process_group()
 
 
+def _fake_score4(pairs):
+    p = np.asarray(pairs, dtype=np.int64)
+    base = ((p[:, 0] * 37 + p[:, 1] * 11) % 500).astype(np.float32)
+    return np.stack([base + 0.1 * k for k in range(4)]).astype(np.float32)
+
+
+def _worker_ef(rank, world, port, tmp, q):
+    """Multi-key plugin (EarlyFusion: four score rows per pair) through the same sharding + single gather."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    os.chdir(tmp)
+    import torch.distributed as dist
+    from acoss_b200.distributed import all_pairwise_distributed
+    from acoss_b200.earlyfusion import EarlyFusion
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(4)
+    feats = []
+    for i, n in enumerate(rng.integers(12, 60, size=11)):
+        feats.append(dict(mfccs=np.zeros((int(n), 4), np.float32), ssms=np.zeros((int(n), 3), np.float32),
+                          chromas=np.zeros((int(n), 12), np.float32), chroma_med=np.zeros(12), label=str(i // 2)))
+    alg = EarlyFusion(None, None, features=feats, shortname="ef%d" % rank, cachedir="cacheef%d" % rank)
+    bounds = all_pairwise_distributed(alg, symmetric=True, score_fn=_fake_score4)
+    q.put((rank, {k: np.array(v) for k, v in alg.Ds.items()}, bounds, alg.pair_weights(alg._pair_array(True))))
+    dist.destroy_process_group()
+
+
+def test_distributed_multikey_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ef, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 11
+    i, j = np.triu_indices(n, k=1)
+    sc = _fake_score4(np.stack([i, j], 1))
+    for rank, Ds, bounds, w in res:
+        assert list(Ds) == ["mfccs", "ssms", "chromas", "early"]
+        for k, key in enumerate(Ds):
+            want = np.zeros((n, n), np.float32)
+            want[i, j] = sc[k]
+            assert np.array_equal(Ds[key], want + want.T), key
+        loads = [w[bounds[r]:bounds[r + 1]].sum() for r in range(world)]
+        assert abs(loads[0] - loads[1]) <= 2 * w.max()      # balanced by cross-similarity cells
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_distributed_all_pairwise_gloo(tmp_path, world):
     import torch.multiprocessing as mp
