@@ -579,12 +579,20 @@ __global__ void __launch_bounds__(128) ef_linestat_kernel(const double *__restri
     double a[KMAX];
 #pragma unroll
     for (int t = 0; t < KMAX; ++t) a[t] = __longlong_as_double(0x7ff0000000000000ll);
-    for (int e = 0; e < len; ++e) {
-        const double v = p[(int64_t)e * stride];
-        if (v < a[KMAX - 1]) {
+    // eight loads in flight per thread (the insertion branch would otherwise serialise the memory latency)
+    for (int e0 = 0; e0 < len; e0 += 8) {
+        double v8[8];
 #pragma unroll
-            for (int t = KMAX - 1; t > 0; --t) a[t] = fmax(a[t - 1], fmin(a[t], v));
-            a[0] = fmin(a[0], v);
+        for (int u = 0; u < 8; ++u)
+            v8[u] = (e0 + u < len) ? p[(int64_t)(e0 + u) * stride] : __longlong_as_double(0x7ff0000000000000ll);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double v = v8[u];
+            if (v < a[KMAX - 1]) {
+#pragma unroll
+                for (int t = KMAX - 1; t > 0; --t) a[t] = fmax(a[t - 1], fmin(a[t], v));
+                a[0] = fmin(a[0], v);
+            }
         }
     }
     double s = 0.0;

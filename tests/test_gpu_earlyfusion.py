@@ -193,3 +193,33 @@ def test_plugin_all_pairwise_and_stats(tmp_path, monkeypatch):
         assert MAP == 1.0 and MR == 1.0
     e.cleanup_memmap()
     e.close()
+
+
+def test_tile_edges_and_long_tracks(eng):
+    """Block counts on and around the 64-wide tile / 32-row quadrant / 8-wide MMA edges, and one track longer
+    than the 1 024 columns the warp-per-row k-NN kernel keeps in registers (falls back to the CTA kernel)."""
+    from oracle import earlyfusion_np as ef
+    rng = np.random.default_rng(77)
+    sizes = [64, 65, 63, 32, 33, 8, 9, 127, 128, 1100]
+    feats = []
+    for nb in sizes:
+        z = np.cumsum(rng.normal(0, 0.4, size=(nb, 4)), axis=0)
+        c = np.abs(np.tanh(z @ rng.normal(size=(4, 24)))) + 0.1 * rng.random((nb, 24))
+        feats.append(dict(mfccs=(z @ rng.normal(size=(4, 17)) + 0.2 * rng.normal(size=(nb, 17))).astype(np.float32),
+                          ssms=(z @ rng.normal(size=(4, 30)) + 0.2 * rng.normal(size=(nb, 30))).astype(np.float32),
+                          chromas=c.astype(np.float32),
+                          chroma_med=np.median(c.astype(np.float32).reshape(-1, 12), axis=0), label="x"))
+    eng.ef_set_tracks(feats)
+    pairs = np.array([(0, 1), (1, 0), (2, 3), (4, 0), (5, 6), (6, 5), (7, 8), (8, 2), (3, 7), (9, 0), (1, 9), (9, 8)],
+                     dtype=np.int32)
+    got = eng.ef_score_pairs(pairs, 0.1, 5)
+    for n, (i, j) in enumerate(pairs):
+        want = ef.similarity_pair(feats[i], feats[j], 0.1, 5)
+        for k, s in enumerate(KINDS):
+            assert got[k, n] == np.float32(want[s]), (sizes[i], sizes[j], s, got[k, n], want[s])
+    # one pair across the long track, matrix level
+    d = eng.ef_dump_pair(8, 9, 0.1, 5)
+    _, mats, bins = ef.similarity_pair(feats[8], feats[9], 0.1, 5, want_matrices=True)
+    for k, s in enumerate(KINDS):
+        assert np.allclose(d["csms"][k], mats[s], rtol=1e-11, atol=1e-13), s
+        assert np.array_equal(d["bins"][k], bins[s]), s
