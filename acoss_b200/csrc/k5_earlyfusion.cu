@@ -389,6 +389,42 @@ __device__ __forceinline__ void ef_dmma(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// 16 k of one 32 x 32 warp quadrant, IMAX x JMAX of its 4 x 4 MMA tiles (compile-time bounds: the skipped
+// tiles are not even issued — a predicated-off DMMA still takes its tensor-pipe slot)
+template <int IMAX, int JMAX>
+__device__ __forceinline__ void ef_quad_mma(const double *Ap, const double *Bp, double (&acc)[4][4][2]) {
+#pragma unroll
+    for (int k4 = 0; k4 < EF_BK; k4 += 4) {
+        double a[IMAX], b[JMAX];
+#pragma unroll
+        for (int i = 0; i < IMAX; ++i) a[i] = Ap[i * 8 * EF3_LD + k4];
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) b[j] = Bp[j * 8 * EF3_LD + k4];
+#pragma unroll
+        for (int i = 0; i < IMAX; ++i)
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) ef_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+template <int IMAX>
+__device__ __forceinline__ void ef_quad_dispatch_j(int jmax, const double *Ap, const double *Bp, double (&acc)[4][4][2]) {
+    switch (jmax) {
+        case 4: ef_quad_mma<IMAX, 4>(Ap, Bp, acc); break;
+        case 3: ef_quad_mma<IMAX, 3>(Ap, Bp, acc); break;
+        case 2: ef_quad_mma<IMAX, 2>(Ap, Bp, acc); break;
+        default: ef_quad_mma<IMAX, 1>(Ap, Bp, acc); break;
+    }
+}
+__device__ __forceinline__ void ef_quad_dispatch(int imax, int jmax, const double *Ap, const double *Bp,
+                                                 double (&acc)[4][4][2]) {
+    switch (imax) {
+        case 4: ef_quad_dispatch_j<4>(jmax, Ap, Bp, acc); break;
+        case 3: ef_quad_dispatch_j<3>(jmax, Ap, Bp, acc); break;
+        case 2: ef_quad_dispatch_j<2>(jmax, Ap, Bp, acc); break;
+        default: ef_quad_dispatch_j<1>(jmax, Ap, Bp, acc); break;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128) ef_csm3_kernel(const double *__restrict__ feat, int dp, int d,
                                                       const double *__restrict__ sq,
@@ -456,34 +492,7 @@ __global__ void __launch_bounds__(128) ef_csm3_kernel(const double *__restrict__
         if (warp_live) {
             const double *Ap = &As[t & 1][32 * wr + g][tg];
             const double *Bp = &Bs[t & 1][32 * wc + g][tg];
-            if (imax == 4 && jmax == 4) {                     // interior quadrant
-#pragma unroll
-                for (int k4 = 0; k4 < EF_BK; k4 += 4) {
-                    double a[4], b[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) a[i] = Ap[i * 8 * EF3_LD + k4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) b[j] = Bp[j * 8 * EF3_LD + k4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) ef_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                }
-            } else {                                          // ragged edge: 8 x 8 MMA tiles past M / N are skipped
-#pragma unroll
-                for (int k4 = 0; k4 < EF_BK; k4 += 4) {
-                    double a[4], b[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) a[i] = Ap[i * 8 * EF3_LD + k4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) b[j] = Bp[j * 8 * EF3_LD + k4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (i < imax && j < jmax) ef_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                }
-            }
+            ef_quad_dispatch(imax, jmax, Ap, Bp, acc);            // ragged edges: only the MMA tiles inside M x N
         }
         __syncthreads();
     }
