@@ -130,6 +130,7 @@ class EarlyFusion(CoverAlgorithm):
         self.all_block_feats = {}
         self._engine = engine
         self._resident = False
+        self.tile_pairs = 1 << 15
         CoverAlgorithm.__init__(self, dataset_csv, name="EarlyFusionTraile", datapath=datapath,
                                 shortname=shortname, cachedir=cachedir,
                                 similarity_types=["mfccs", "ssms", "chromas", "early"], features=features)
@@ -170,6 +171,24 @@ class EarlyFusion(CoverAlgorithm):
             self.times['raw'].append((time.time() - tic) / len(idxs))
         for k, s in enumerate(Engine.EF_KINDS):
             self.Ds[s][idxs[:, 0], idxs[:, 1]] = scores[k]
+
+    def all_pairwise(self, parallel=0, n_cores=12, symmetric=False, precomputed=False):
+        """algorithm_template.py:142-192 with the pair fan-out batched for the GPU: tiles of ``tile_pairs``
+        pairs per ``similarity`` call instead of the reference's 45 joblib chunks (``parallel`` / ``n_cores`` are
+        accepted and ignored: a CUDA context must not be forked)."""
+        h5filename = "%s_Ds.h5" % self.get_cacheprefix()
+        if precomputed:
+            self.Ds = self._load_Ds(h5filename)
+            self.get_all_clique_ids()
+            return
+        all_pairs = self._pair_array(symmetric)
+        self._ensure_resident()                    # loads every song => cliques are complete
+        for k0 in range(0, len(all_pairs), self.tile_pairs):
+            self.similarity(all_pairs[k0:k0 + self.tile_pairs])
+        if symmetric:
+            for similarity_type in self.Ds:
+                self.Ds[similarity_type] += self.Ds[similarity_type].T
+        self._save_Ds(h5filename)
 
     # -- hooks of acoss_b200.distributed.all_pairwise_distributed (one process per GPU) -----------------
     def pair_weights(self, pairs):

@@ -223,3 +223,23 @@ def test_tile_edges_and_long_tracks(eng):
     for k, s in enumerate(KINDS):
         assert np.allclose(d["csms"][k], mats[s], rtol=1e-11, atol=1e-13), s
         assert np.array_equal(d["bins"][k], bins[s]), s
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_randomised_shapes(eng, seed):
+    """Seeded random block counts, dimensions, kappa and K: all four scores of all pairs equal the oracle's."""
+    from acoss_b200 import synthetic
+    from oracle import earlyfusion_np as ef
+    rng = np.random.default_rng(1000 + seed)
+    dims = dict(mfccs=int(rng.integers(5, 130)), ssms=int(rng.integers(5, 130)), chromas=12 * int(rng.integers(1, 9)))
+    feats = synthetic.ef_dataset([2, 1, 1], int(rng.integers(30, 180)), 500 + seed, dims=dims, jitter=0.5,
+                                 dtype=np.float32 if seed % 2 else np.float64)
+    kappa = float(rng.choice([0.05, 0.1, 0.2]))
+    K = int(rng.integers(2, 14))
+    eng.ef_set_tracks(feats)
+    pairs = np.array([(i, j) for i in range(len(feats)) for j in range(len(feats)) if i != j], dtype=np.int32)
+    got = eng.ef_score_pairs(pairs, kappa, K)
+    for n, (i, j) in enumerate(pairs):
+        want = ef.similarity_pair(feats[i], feats[j], kappa, K)
+        for k, s in enumerate(KINDS):
+            assert got[k, n] == np.float32(want[s]), (seed, i, j, s, got[k, n], want[s])
