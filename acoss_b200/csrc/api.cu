@@ -61,7 +61,7 @@ struct acoss_ctx {
     std::vector<int64_t> ef_hoff;
     int32_t ef_d[3] = {0, 0, 0}, ef_dp[3] = {0, 0, 0};
     int32_t ef_tracks = 0;
-    Buf ef_csm, ef_stat, ef_shapes, ef_nn, ef_csmoff, ef_oti, ef_pairs, ef_scores, ef_bits, ef_bitoff;
+    Buf ef_csm, ef_stat, ef_shapes, ef_nn, ef_csmoff, ef_oti, ef_pairs, ef_scores, ef_bits, ef_bitoff, ef_stage;
     int64_t ef_stats[4] = {0, 0, 0, 0};
 };
 
@@ -166,7 +166,7 @@ int acoss_destroy(acoss_ctx *c) {
                    &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap, &c->dbg,
                    &c->ef_feat[0], &c->ef_feat[1], &c->ef_feat[2], &c->ef_sq[0], &c->ef_sq[1], &c->ef_cmed, &c->ef_off,
                    &c->ef_csm, &c->ef_stat, &c->ef_shapes, &c->ef_nn, &c->ef_csmoff, &c->ef_oti, &c->ef_pairs,
-                   &c->ef_scores, &c->ef_bits, &c->ef_bitoff};
+                   &c->ef_scores, &c->ef_bits, &c->ef_bitoff, &c->ef_stage};
     for (Buf *b : bufs) free_buf(*b);
     if (c->own_frames && c->d_frames) cudaFree(c->d_frames);
     if (c->d_offsets) cudaFree(c->d_offsets);
@@ -734,20 +734,16 @@ int acoss_ef_set_tracks(acoss_ctx *c, const void *mfccs, int32_t d_mfccs, const 
     const int64_t rows = offsets[n_tracks];
     const void *src[3] = {mfccs, ssms, chromas};
     const int32_t d[3] = {d_mfccs, d_ssms, d_chromas};
-    Buf stage;
+    Buf &stage = c->ef_stage;                                  // upload staging, released below (also by acoss_destroy)
     for (int k = 0; k < 3; ++k) {
         const int dp = (d[k] + 15) / 16 * 16;
-        int rc = ensure(c->ef_feat[k], (size_t)rows * dp * 8);
-        if (rc == ACOSS_OK) rc = ensure(stage, (size_t)rows * d[k] * elem_size);
-        if (rc == ACOSS_OK && k < 2) rc = ensure(c->ef_sq[k], (size_t)rows * 8);
-        if (rc != ACOSS_OK) { free_buf(stage); return rc; }
-        cudaError_t e = cudaMemcpyAsync(stage.p, src[k], (size_t)rows * d[k] * elem_size, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) { free_buf(stage); acoss_set_error("ef_set_tracks: H2D copy failed: %s", cudaGetErrorString(e)); return ACOSS_E_CUDA; }
-        rc = launch_ef_widen(stage.p, elem_size, rows, d[k], dp, (double *)c->ef_feat[k].p, st);
-        if (rc == ACOSS_OK) rc = launch_ef_rownorm((double *)c->ef_feat[k].p, rows, dp, k == 2 ? 1 : 0, k < 2 ? (double *)c->ef_sq[k].p : nullptr, st);
-        if (rc != ACOSS_OK) { free_buf(stage); return rc; }
-        e = cudaStreamSynchronize(st);                  // the staging buffer is reused by the next kind
-        if (e != cudaSuccess) { free_buf(stage); acoss_set_error("ef_set_tracks: %s", cudaGetErrorString(e)); return ACOSS_E_CUDA; }
+        TRY(ensure(c->ef_feat[k], (size_t)rows * dp * 8));
+        TRY(ensure(stage, (size_t)rows * d[k] * elem_size));
+        if (k < 2) TRY(ensure(c->ef_sq[k], (size_t)rows * 8));
+        CUDA_TRY(cudaMemcpyAsync(stage.p, src[k], (size_t)rows * d[k] * elem_size, cudaMemcpyHostToDevice, st));
+        TRY(launch_ef_widen(stage.p, elem_size, rows, d[k], dp, (double *)c->ef_feat[k].p, st));
+        TRY(launch_ef_rownorm((double *)c->ef_feat[k].p, rows, dp, k == 2 ? 1 : 0, k < 2 ? (double *)c->ef_sq[k].p : nullptr, st));
+        CUDA_TRY(cudaStreamSynchronize(st));                  // the staging buffer is reused by the next kind
         c->ef_d[k] = d[k];
         c->ef_dp[k] = dp;
     }
