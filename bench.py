@@ -19,6 +19,9 @@ Output: ONE JSON line on rank 0 (contract in the task statement), with
                the lane-instruction issue peak as well
   cpu_baseline the oracle's plain-C port of the reference CPU path (oracle/serra09_c.c), all host
                threads, on a bounded sample of the same pairs
+  earlyfusion  (N=1 only, informational, after the timed region) the EarlyFusion pair scoring on a covers80-shaped
+               slice (BASELINE.json configs[1]): its own e2e, tensor roofline of the float64 DMMA kernel and numpy
+               oracle sample; `--no-earlyfusion` skips it
 `--impl reference` times that CPU port alone (the reference's essentia path cannot be installed:
 DESIGN.md §5) on the same config/metric/unit.
 """
@@ -119,6 +122,55 @@ def algorithmic_bytes(lens, pairs, incr=9):
     return int(cells.sum()), int(k2.sum()), int(k3.sum())
 
 
+def earlyfusion_leg(eng, sm_mhz):
+    """Secondary, informational leg: the full EarlyFusion pair scoring (acoss_ef_score_pairs: float64 DMMA
+    cross-similarity matrices -> getWCSM fusion -> k-NN binarisation -> Smith-Waterman, four scores per pair) on a
+    covers80-shaped slice (96 tracks x ~400 beat-synchronous blocks, the reference's block dimensions), host pair
+    list in / host scores out, with the numpy oracle timed on a few of the same pairs.  DESIGN.md 4.5."""
+    from acoss_b200 import synthetic
+    from oracle import earlyfusion_np as ef
+    feats = synthetic.ef_dataset([2] * 48, 400, 20242)
+    n = len(feats)
+    i, j = np.triu_indices(n, k=1)
+    pairs = np.stack([i, j], axis=1).astype(np.int32)
+    nb = np.array([f["mfccs"].shape[0] for f in feats], dtype=np.int64)
+    cells = int((nb[pairs[:, 0]] * nb[pairs[:, 1]]).sum())
+    dsum = sum(feats[0][k].shape[1] for k in ("mfccs", "ssms", "chromas"))
+    eng.ef_set_tracks(feats)
+    eng.ef_score_pairs(pairs[:64])
+    eng.ef_score_pairs(pairs)
+    eng.set_profiling(True)
+    reps, times = 3, []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        got = eng.ef_score_pairs(pairs)
+        times.append(time.perf_counter() - t0)
+    ms = eng.ef_stage_ms()
+    st = eng.ef_last_stats()
+    eng.set_profiling(False)
+    csm_tflops = 2.0 * cells * dsum / (ms["csm"] / reps * 1e-3) / 1e12
+    peak_tflops = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12            # 64 float64 FMA / clk / SM (DFMA and DMMA alike)
+    sel = np.random.default_rng(2).choice(len(pairs), size=6, replace=False)
+    t0 = time.perf_counter()
+    same = True
+    for k in sel:
+        w = ef.similarity_pair(feats[pairs[k, 0]], feats[pairs[k, 1]])
+        same &= all(got[q, k] == np.float32(w[s]) for q, s in enumerate(("mfccs", "ssms", "chromas", "early")))
+    tc = time.perf_counter() - t0
+    return {"workload": "EarlyFusion pair scoring: %d tracks x ~400 blocks, dims 1000/1225/480 float32, %d pairs per call"
+                        % (n, len(pairs)),
+            "e2e": {"value": len(pairs) / min(times), "unit": UNIT, "h2d_bytes_per_step": int(pairs.nbytes),
+                    "d2h_bytes_per_step": int(got.nbytes), "api": "Engine.ef_score_pairs (acoss_ef_score_pairs), host buffers"},
+            "device_ms_per_call": {k: v / reps for k, v in ms.items()}, "gpu_launches_per_call": st["launches"],
+            "roofline": {"bound": "tensor", "kernel": "ef_csm3_kernel (float64 DMMA cross-similarity contraction)",
+                         "achieved": csm_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": csm_tflops / peak_tflops,
+                         "peak_kind": "nominal float64 rate (64 FMA/clk/SM x 148 SMs) at the sampled SM clock",
+                         "traffic": None, "note": "achieved counts 2*M*N*d flops of the pair matrices only (tile padding excluded)"},
+            "cpu_baseline": {"value": len(sel) / tc, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d pairs through the numpy oracle (BLAS threads), %.1f s" % (len(sel), tc),
+                             "parity_on_sample": bool(same)}}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU port of the reference path, all host threads, bounded steps."""
     if rank != 0:
@@ -163,6 +215,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-earlyfusion", action="store_true", help="skip the secondary EarlyFusion leg")
     ap.add_argument("--crp-path", default="auto", choices=["auto", "exact"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -320,6 +373,14 @@ def main():
                "gcups": algorithmic_bytes(lens, idx)[0] / tc / 1e9,
                "parity_on_sample": bool(np.array_equal(got, ref_scores))}
 
+    # ---- secondary workload (not the headline): EarlyFusion pair scoring, BASELINE.json configs[1] shape ----
+    ef_line = None
+    if rank == 0 and world == 1 and not args.no_earlyfusion:
+        try:
+            ef_line = earlyfusion_leg(eng, (clocks or {}).get("sm_mhz") or sm_max)
+        except Exception as e:                                  # never let the extra leg break the headline line
+            ef_line = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -333,7 +394,8 @@ def main():
                         "api": "acoss_b200.serra09.Serra09.similarity(idxs) -> host score matrix"},
                 "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "roofline_alu": roofline_alu, "cpu_baseline": cpu,
-                "fallback_pairs": eng.last_stats()["fallback_pairs"], "k2_debug": k2_debug}
+                "fallback_pairs": eng.last_stats()["fallback_pairs"], "k2_debug": k2_debug,
+                "earlyfusion": ef_line}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
