@@ -318,7 +318,8 @@ static int check_params(const acoss_ctx *c, const acoss_params *p) {
     if (p->m < 1 || p->m > 64 || p->tau < 1 || p->tau > 64) { acoss_set_error("m and tau must be in 1..64"); return ACOSS_E_INVALID; }
     if (!(p->kappa >= 0.f && p->kappa <= 1.f)) { acoss_set_error("kappa must be in [0,1]"); return ACOSS_E_INVALID; }
     if (p->noti < 0 || p->noti > 64) { acoss_set_error("noti out of range"); return ACOSS_E_INVALID; }
-    if (p->align != ACOSS_ALIGN_QMAX && p->align != ACOSS_ALIGN_DMAX && p->align != ACOSS_ALIGN_DMAX_PLAIN) {
+    if (p->align != ACOSS_ALIGN_QMAX && p->align != ACOSS_ALIGN_DMAX && p->align != ACOSS_ALIGN_DMAX_PLAIN &&
+        p->align != ACOSS_ALIGN_SW) {
         acoss_set_error("align mode %d not implemented for the pair pipeline", p->align);
         return ACOSS_E_INVALID;
     }
@@ -441,17 +442,8 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
                                 (float *)c->thr_q.p, (float *)c->thr_r.p, status, nullptr, st, &launches));
         }
         t2.stop();
-        StageTimer t3(c, 2);
-        TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p,
-                           (const int32_t *)c->cols.p, n, g.max_cols, scores2_dev ? ACOSS_ALIGN_QMAX : p->align,
-                           p->gamma_o, p->gamma_e, scores_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
-        if (scores2_dev)
-            TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p,
-                               (const int32_t *)c->cols.p, n, g.max_cols, ACOSS_ALIGN_DMAX, p->gamma_o, p->gamma_e,
-                               scores2_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
-        t3.stop();
         if (dump && first == 0) {
-            // single-pair debug dump (K == 1)
+            // single-pair debug dump (K == 1); before the DP stage: the SW trim below edits rows / cols / CRP
             const int q = 0;
             (void)q;
             if (dump->oti) CUDA_TRY(cudaMemcpyAsync(dump->oti, c->oti.p, 4, cudaMemcpyDeviceToHost, st));
@@ -467,6 +459,19 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
             if (dump->thr_r) CUDA_TRY(cudaMemcpyAsync(dump->thr_r, c->thr_r.p, (size_t)rc[1] * 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         }
+        StageTimer t3(c, 2);
+        if (!scores2_dev && p->align == ACOSS_ALIGN_SW) {        // SW drops the last row / column of the CRP
+            TRY(launch_sw_trim((uint32_t *)c->crp.p, g.crp_words, g.words, (int32_t *)c->rows.p, (int32_t *)c->cols.p, n, st));
+            ++launches;
+        }
+        TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p,
+                           (const int32_t *)c->cols.p, n, g.max_cols, scores2_dev ? ACOSS_ALIGN_QMAX : p->align,
+                           p->gamma_o, p->gamma_e, scores_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
+        if (scores2_dev)
+            TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p,
+                               (const int32_t *)c->cols.p, n, g.max_cols, ACOSS_ALIGN_DMAX, p->gamma_o, p->gamma_e,
+                               scores2_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
+        t3.stop();
     }
     // fold per-pair status into one word; read back at sync time
     or_reduce_kernel<<<148, 256, 0, st>>>(status, K, (uint32_t *)c->misc.p);

@@ -95,6 +95,8 @@ int launch_dp_bits(const uint32_t *bits, int64_t slot_words, int words_per_row, 
 // pair geometry (rows = n_q - m*tau, cols = n_r - m*tau) for pairs[first..first+n)
 int launch_pair_geometry(const TrackSet &ts, const int32_t *pairs, int64_t first, int n, int incr,
                          int32_t *rows, int32_t *cols, cudaStream_t st);
+int launch_sw_trim(uint32_t *bits, int64_t slot_words, int words_per_row, int32_t *rows, int32_t *cols, int n,
+                   cudaStream_t st);
 int launch_pack_bytes(const uint8_t *mats, const int64_t *offsets, const int32_t *shapes, int n,
                       int mode, uint32_t *bits, int64_t slot_words, int words_per_row,
                       int32_t *rows, int32_t *cols, uint32_t *nonbinary_flag, cudaStream_t st);

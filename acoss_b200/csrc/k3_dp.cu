@@ -555,6 +555,31 @@ int launch_pair_geometry(const TrackSet &ts, const int32_t *pairs, int64_t first
     return ACOSS_OK;
 }
 
+// Smith-Waterman over a CRP the pair pipeline emitted (BASELINE.json configs[1]: "Smith-Waterman on the same
+// binary CRPs"): smith_waterman_constrained never reads the last row / column of its input
+// (alignment_tools.py:36-39: B[i-1][j-1], i < M, j < N), so the DP matrix is (rows - 1) x (cols - 1) and the bit
+// of column cols - 1 is cleared (the packed DP kernel relies on zero bits past its last column).
+__global__ void __launch_bounds__(128) sw_trim_kernel(uint32_t *__restrict__ bits, int64_t slot_words, int wpr,
+                                                      int32_t *__restrict__ rows, int32_t *__restrict__ cols) {
+    const int k = blockIdx.x;
+    const int R = rows[k], C = cols[k];
+    if (C >= 1) {
+        const int w = (C - 1) >> 5;
+        const unsigned keep = ~(1u << ((C - 1) & 31));
+        for (int i = threadIdx.x; i < R; i += blockDim.x) bits[(int64_t)k * slot_words + (int64_t)i * wpr + w] &= keep;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { rows[k] = R > 0 ? R - 1 : 0; cols[k] = C > 0 ? C - 1 : 0; }
+}
+
+int launch_sw_trim(uint32_t *bits, int64_t slot_words, int words_per_row, int32_t *rows, int32_t *cols, int n,
+                   cudaStream_t st) {
+    if (n <= 0) return ACOSS_OK;
+    sw_trim_kernel<<<n, 128, 0, st>>>(bits, slot_words, words_per_row, rows, cols);
+    CUDA_TRY(cudaGetLastError());
+    return ACOSS_OK;
+}
+
 int launch_pack_bytes(const uint8_t *mats, const int64_t *offsets, const int32_t *shapes, int n, int mode,
                       uint32_t *bits, int64_t slot_words, int words_per_row, int32_t *rows, int32_t *cols,
                       uint32_t *nonbinary_flag, cudaStream_t st) {

@@ -58,7 +58,8 @@ typedef struct acoss_params {
     int32_t noti;           /* 12                                                                  */
     float gamma_o;          /* disOnset, 0.5                                                       */
     float gamma_e;          /* disExtension, 0.5                                                   */
-    int32_t align;          /* ACOSS_ALIGN_QMAX (Serra09) or ACOSS_ALIGN_DMAX (ChenFusion)         */
+    int32_t align;          /* ACOSS_ALIGN_QMAX (Serra09), ACOSS_ALIGN_DMAX (ChenFusion) or        */
+                            /* ACOSS_ALIGN_SW: smith_waterman_constrained over the same CRP        */
     int32_t integer_guard;  /* F1 switch: 0 = essentia behaviour (integer rank -> threshold 0)     */
     int32_t crp_path;       /* ACOSS_CRP_AUTO / ACOSS_CRP_EXACT                                    */
 } acoss_params;

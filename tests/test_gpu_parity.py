@@ -245,3 +245,34 @@ def test_chen_pairs_both_scores(eng):
     wq, wd = oc.chen_pairs(frames, offs, pairs, nthreads=8)
     assert np.array_equal(q, wq) and np.array_equal(d, wd)
     assert np.array_equal(q, eng.score_pairs(pairs))
+
+
+# ------------------------------------------------------------------------------------------- C2: SW over emitted CRPs
+@pytest.mark.parametrize("path", ["auto", "exact"])
+def test_sw_over_emitted_crps(eng, path):
+    """BASELINE.json configs[1]: Smith-Waterman (alignment_tools.py:26-46) over the binary CRPs the Serra09
+    stage emits, as one batched pair-pipeline call (align = ACOSS_ALIGN_SW) — against the oracle's SW of the
+    oracle's CRP of every pair; ragged lengths incl. CRPs with fewer than 4 rows / columns (score 0.0)."""
+    from acoss_b200 import default_params, synthetic
+    from acoss_b200._lib import CRP_AUTO, CRP_EXACT
+    from acoss_b200.engine import ALIGN_SW
+    from oracle import earlyfusion_np as ef
+    from oracle import serra09_c as oc
+    tracks, _ = synthetic.config_dataset("tiny")
+    rng = np.random.default_rng(3)
+    tracks = list(tracks[:9]) + [hp(rng, n) for n in (11, 12, 13, 40, 1040)]
+    _set(eng, tracks)
+    pairs = np.array([(i, j) for i in range(len(tracks)) for j in range(len(tracks)) if i != j], np.int32)
+    p = default_params(align=ALIGN_SW, crp_path=CRP_EXACT if path == "exact" else CRP_AUTO)
+    got = eng.score_pairs(pairs, p)
+    want = np.empty(len(pairs), np.float32)
+    for k, (i, j) in enumerate(pairs):
+        _, dbg = oc.pair(tracks[i], tracks[j], want_debug=True)
+        want[k] = ef.smith_waterman_constrained_x10(dbg["crp"]) / 10.0
+    assert np.array_equal(got, want)
+    assert (want > 0).any() and (want == 0).any()
+    # the debug dump of a pair is unaffected by the SW trim: full CRP, SW score
+    d = eng.dump_pair(0, 1, p)
+    _, dbg = oc.pair(tracks[0], tracks[1], want_debug=True)
+    assert np.array_equal(d["crp"], dbg["crp"])
+    assert d["score"] == np.float32(ef.smith_waterman_constrained_x10(dbg["crp"]) / 10.0)
