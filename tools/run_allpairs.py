@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--oracle-sample", type=int, default=256, help="pairs re-scored by the CPU oracle (0 = skip)")
     ap.add_argument("--tile", type=int, default=1 << 18, help="pairs per engine call")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--align", default="qmax", choices=["qmax", "sw"],
+                    help="alignment over the CRPs: Serra09's Qmax, or smith_waterman_constrained (BASELINE configs[1], C2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -66,6 +68,9 @@ def main():
     eng.set_tracks(frames, offs)
     t_upload = time.perf_counter() - t0
 
+    from acoss_b200.engine import ALIGN_QMAX, ALIGN_SW
+    run_params = default_params(align=ALIGN_SW if args.align == "sw" else ALIGN_QMAX)
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -75,7 +80,7 @@ def main():
     t0 = time.perf_counter()
     parts, fallbacks = [], 0
     for k in range(0, len(mine), args.tile):
-        parts.append(eng.score_pairs(mine[k:k + args.tile], default_params()))
+        parts.append(eng.score_pairs(mine[k:k + args.tile], run_params))
         fallbacks += eng.last_stats()["fallback_pairs"]
     local_scores = np.concatenate(parts) if parts else np.zeros(0, np.float32)
     sync_all()
@@ -91,7 +96,7 @@ def main():
         sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         t_score, t_gather, fallbacks = float(mx[0]), float(mx[1]), int(sm[2])
     if rank == 0:
-        out = dict(config=args.config, n_gpus=world, tracks=N, pairs=int(len(pairs)), cells=int(cells.sum()),
+        out = dict(config=args.config, align=args.align, n_gpus=world, tracks=N, pairs=int(len(pairs)), cells=int(cells.sum()),
                    mean_frames=float(lens.mean()), t_generate_s=t_gen, t_upload_s=t_upload, t_score_s=t_score,
                    t_gather_s=t_gather, pairs_per_s=len(pairs) / t_score, gcups=float(cells.sum()) / t_score / 1e9,
                    fallback_pairs=fallbacks, shard_pairs=[int(x) for x in np.diff(bounds)])
@@ -99,7 +104,12 @@ def main():
             from oracle import serra09_c as oc
             sel = np.random.default_rng(3).permutation(len(pairs))[:args.oracle_sample]
             t0 = time.perf_counter()
-            want = oc.pairs(frames, offs, pairs[sel], nthreads=os.cpu_count() or 1)
+            if args.align == "sw":                             # oracle CRP of each sampled pair -> oracle SW
+                from oracle import earlyfusion_np as ef
+                want = np.array([ef.smith_waterman_constrained_x10(
+                    oc.pair(tracks[a], tracks[b], want_debug=True)[1]["crp"]) / 10.0 for a, b in pairs[sel]], np.float32)
+            else:
+                want = oc.pairs(frames, offs, pairs[sel], nthreads=os.cpu_count() or 1)
             out["oracle_sample"] = dict(pairs=int(len(sel)), identical=bool(np.array_equal(want, full[sel])),
                                         cpu_s=time.perf_counter() - t0, cores=os.cpu_count())
         if not args.no_eval:
