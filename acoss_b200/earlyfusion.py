@@ -23,11 +23,12 @@ semantics for callers that need a single matrix — the plugin itself does not u
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
 from . import _lib
-from .algorithm_template import CoverAlgorithm
+from .algorithm_template import CoverAlgorithm, _load_feature_file
 from .engine import Engine
 
 __all__ = ["EarlyFusion", "nneighbs", "sw_of_csms"]
@@ -140,10 +141,26 @@ class EarlyFusion(CoverAlgorithm):
 
     def load_features(self, i):
         """Precomputed block features of song i (what the reference's load_features returns,
-        earlyfusion_traile.py:66-155); records the clique as a side effect."""
-        if i not in self.all_block_feats:
-            self.all_block_feats[i] = CoverAlgorithm.load_features(self, i)
-        return self.all_block_feats[i]
+        earlyfusion_traile.py:66-155); records the clique as a side effect.  Lookup order of the reference
+        (:84-97): the in-memory cache, then the per-song cache file ``<cacheprefix>_<i>.h5`` the reference
+        writes after computing the blocks (read through deepdish when importable, else the same dictionary as
+        ``<cacheprefix>_<i>.npz``), then the feature dictionary of the song itself, which must already hold the
+        block features (the beat-synchronous block computation is not part of this package)."""
+        if i in self.all_block_feats:
+            return self.all_block_feats[i]
+        cached = "%s_%i.h5" % (self.get_cacheprefix(), i)
+        feats = None
+        if self._features is None and (os.path.exists(cached) or os.path.exists(cached[:-3] + ".npz")):
+            feats = _load_feature_file(cached)
+            CoverAlgorithm.load_features(self, i)               # clique info as a side effect (:95-96)
+        else:
+            feats = CoverAlgorithm.load_features(self, i)
+        missing = [k for k in ("mfccs", "ssms", "chromas", "chroma_med") if k not in feats]
+        if missing:
+            raise KeyError("song %d has no precomputed block features %r; compute them with the reference's "
+                           "EarlyFusion.load_features (madmom / skimage on-ramp) first" % (i, missing))
+        self.all_block_feats[i] = feats
+        return feats
 
     def engine(self) -> Engine:
         if self._engine is None:

@@ -172,3 +172,30 @@ def test_chenfusion_signature_and_normalize(workdir):
         assert np.array_equal(np.asarray(c.Ds[key]), want)
     with pytest.raises(NotImplementedError):               # SNF late fusion is outside the hot path
         c.do_late_fusion()
+
+
+def test_earlyfusion_load_features_lookup_order(workdir):
+    """EarlyFusion.load_features (earlyfusion_traile.py:84-97): memory cache, then <cacheprefix>_<i> cache file,
+    then the song's own dictionary; the clique side effect happens in every case; missing blocks are an error."""
+    rng = np.random.default_rng(0)
+    def blocks(nb):
+        return dict(mfccs=rng.random((nb, 8)).astype(np.float32), ssms=rng.random((nb, 6)).astype(np.float32),
+                    chromas=rng.random((nb, 12)).astype(np.float32), chroma_med=rng.random(12).astype(np.float32))
+    feats = [dict(blocks(20), label="a"), dict(blocks(22), label="a"), dict(hpcp=np.zeros((5, 12)), label="b")]
+    e = efp.EarlyFusion(None, None, features=feats, shortname="lf")
+    f0 = e.load_features(0)
+    assert f0 is e.load_features(0) and set(("mfccs", "ssms", "chromas", "chroma_med")) <= set(f0)
+    e.load_features(1)
+    assert e.cliques == {"a": {0, 1}}
+    with pytest.raises(KeyError):
+        e.load_features(2)
+    # file-backed: raw feature file without blocks + the reference-style per-song cache file next to the score matrices
+    os.makedirs("data/w1", exist_ok=True)
+    with open("ds.csv", "w") as f:
+        f.write("work_id,track_id\nw1,t1\n")
+    np.savez("data/w1/t1.npz", hpcp=np.zeros((5, 12), np.float32), label="w1")
+    e2 = efp.EarlyFusion("ds.csv", "data/", shortname="lf2")
+    b = blocks(9)
+    np.savez("%s_0.npz" % e2.get_cacheprefix(), **b)
+    got = e2.load_features(0)
+    assert np.array_equal(got["mfccs"], b["mfccs"]) and e2.cliques == {"w1": {0}}
