@@ -13,9 +13,15 @@
 // Arithmetic: float64 throughout (the reference's numba/numpy code computes in the dtype of its
 // inputs; its float32 features make BLAS-order-dependent float32 CSMs — the float64 value is the
 // one every BLAS approximates, and it is what the pinned oracle computes).  These are genuine
-// GEMMs (K = 480 / 1000 / 1225) but float64 ones: B200 issues DFMA at 64 lanes/clk/SM and has no
-// faster float64 tensor path, so the contraction is a register-tiled DFMA kernel (64x64 CTA tile,
-// 8x4 accumulators per thread, k-major shared-memory tiles read with broadcast LDS.128).
+// GEMMs (K = 480 / 1000 / 1225) but float64 ones, so tcgen05 (no float64 kind) does not apply; the
+// float64 tensor path of sm_100a is the warp-level DMMA.  Three generations of the contraction live
+// here, selectable with ACOSS_EF_CSM=1|2|3 for A/B timing (profiles/r1_ef.md):
+//   1  ef_csm_kernel   DFMA, 8x4 register tiles, k-major shared tiles          13.7 TFLOP/s
+//   2  ef_csm2_kernel  DFMA, 8x8 register tiles, row-major cp.async tiles      19.6 TFLOP/s
+//   3  ef_csm3_kernel  DMMA m8n8k4, 2x2 warps of 32x32, cp.async (production)   30.4 TFLOP/s
+// The DFMA kernels add the k terms of a cell in ascending k, one fused multiply-add per term; inside one DMMA the
+// order over its 4 k is the hardware's (the tests bound every matrix to 1e-11 of the oracle and check that the
+// matrices of (i, j) and (j, i) are exact transposes).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(128) ef_csm_kernel(const double *__restrict__ 
 // touches exactly 128 distinct bytes (B) or 32 (A): 32 wavefronts per 128 DFMA per warp, half the pipe.
 // Global -> shared goes through cp.async (16 B chunks, two-stage ring), no staging registers.  The k order
 // of every accumulator is unchanged (k ascending, one FMA per k), so the results are bit-identical to the
-// first-generation kernel.
+// first-generation kernel's.
 // ---------------------------------------------------------------------------------------------
 #define EF2_LD 18
 #define EF2_MAXDP 2048   // widest (padded) chroma block the rolled-column map covers
