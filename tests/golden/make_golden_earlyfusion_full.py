@@ -42,7 +42,11 @@ CASES = [
     ("f64_full", [2, 1], 90, 302, None, "float64", 0.1, 10),
     ("f64_k5", [3], 55, 303, dict(mfccs=40, ssms=28, chromas=24), "float64", 0.15, 5),
     ("f32_full", [2, 1], 90, 302, None, "float32", 0.1, 10),
+    ("f64_count", [2, 1, 1], 45, 304, dict(mfccs=30, ssms=21, chromas=36), "float64", 6, 4),      # kappa >= 1: a count
+    ("f32_small", [3, 1], 60, 305, dict(mfccs=50, ssms=36, chromas=60), "float32", 0.2, 12),
+    ("f64_ragged", [2, 2], 80, 306, dict(mfccs=24, ssms=15, chromas=12), "float64", 0.05, 8),
 ]
+JITTER = {"f64_ragged": 0.6}
 
 
 def pack(B):
@@ -74,7 +78,8 @@ def main():
 
         names = []
         for name, cliques, nb, seed, dims, dtype, kappa, K in CASES:
-            feats = synthetic.ef_dataset(cliques, nb, seed, dims=dims, dtype=np.dtype(dtype))
+            feats = synthetic.ef_dataset(cliques, nb, seed, dims=dims, dtype=np.dtype(dtype),
+                                         jitter=JITTER.get(name, 0.15))
             n = len(feats)
             ef = eft.EarlyFusion.__new__(eft.EarlyFusion)
             ef.name, ef.shortname, ef.cachedir, ef.chroma_type = "EarlyFusionTraile", "golden", tmp, "hpcp"

@@ -20,7 +20,11 @@ EF_FULL_CASES = [
     ("f64_full", [2, 1], 90, 302, None, "float64", 0.1, 10),
     ("f64_k5", [3], 55, 303, dict(mfccs=40, ssms=28, chromas=24), "float64", 0.15, 5),
     ("f32_full", [2, 1], 90, 302, None, "float32", 0.1, 10),
+    ("f64_count", [2, 1, 1], 45, 304, dict(mfccs=30, ssms=21, chromas=36), "float64", 6, 4),
+    ("f32_small", [3, 1], 60, 305, dict(mfccs=50, ssms=36, chromas=60), "float32", 0.2, 12),
+    ("f64_ragged", [2, 2], 80, 306, dict(mfccs=24, ssms=15, chromas=12), "float64", 0.05, 8),
 ]
+EF_JITTER = {"f64_ragged": 0.6}
 
 
 @pytest.fixture(scope="module")
@@ -45,7 +49,7 @@ def test_scores_match_reference_golden(eng, gfull, case):
     """Device scores == what the reference's EarlyFusion.similarity stored in Ds (float32), all pairs."""
     from acoss_b200 import synthetic
     name, cliques, nb, seed, dims, dtype, kappa, K = case
-    feats = synthetic.ef_dataset(cliques, nb, seed, dims=dims, dtype=np.dtype(dtype))
+    feats = synthetic.ef_dataset(cliques, nb, seed, dims=dims, dtype=np.dtype(dtype), jitter=EF_JITTER.get(name, 0.15))
     eng.ef_set_tracks(feats)
     pairs = _all_pairs(len(feats))
     got = eng.ef_score_pairs(pairs, kappa, K)
