@@ -16,9 +16,8 @@ therefore returns precomputed block features exactly as the reference's returns 
 ``do_late_fusion`` (N x N similarity-network fusion of finished score matrices) is delegated to the
 reference's function when the ``acoss`` package is importable.
 
-``sw_of_csms`` scores caller-supplied float64 cross-similarity matrices (``acoss_knn_sw``); ``get_oti`` /
-``csm_euclidean`` / ``csm_cosine`` / ``csm_blocked_oti`` are small host utilities with the reference's
-semantics for callers that need a single matrix — the plugin itself does not use them.
+``sw_of_csms`` scores caller-supplied float64 cross-similarity matrices on the GPU (``acoss_knn_sw``).  There is
+no host (numpy) implementation of any stage in this package: without the CUDA library every call raises.
 """
 from __future__ import annotations
 
@@ -73,39 +72,6 @@ def sw_of_csms(engine: Engine, csms, kappa, want_bits=False):
         mats.append(np.unpackbits(w.view(np.uint8), axis=1, bitorder="little")[:, :N])
         o += M * W
     return scores, mats
-
-
-def get_oti(C1, C2) -> int:
-    """argmax_i sum(roll(C1, i) * C2), first max (cross_recurrence.py:94-103)."""
-    C1 = np.asarray(C1, dtype=np.float64)
-    C2 = np.asarray(C2, dtype=np.float64)
-    scores = np.zeros(len(C1))
-    for i in range(len(C1)):
-        scores[i] = np.sum(np.roll(C1, i) * C2)
-    return int(np.argmax(scores))
-
-
-def csm_euclidean(X, Y):
-    """sqrt(max(0, |x|^2 + |y|^2 - 2 X Y^T)) (cross_recurrence.py:45-48)."""
-    C = np.sum(X ** 2, 1)[:, None] + np.sum(Y ** 2, 1)[None, :] - 2 * X.dot(Y.T)
-    C[C < 0] = 0
-    return np.sqrt(C)
-
-
-def csm_cosine(X, Y):
-    """1 - Xhat Yhat^T with zero norms replaced by 1 (cross_recurrence.py:67-73)."""
-    xn = np.sqrt(np.sum(X ** 2, 1)); xn[xn == 0] = 1
-    yn = np.sqrt(np.sum(Y ** 2, 1)); yn[yn == 0] = 1
-    return 1 - (X / xn[:, None]).dot((Y / yn[:, None]).T)
-
-
-def csm_blocked_oti(X, Y, C1, C2, csm_fn=csm_cosine):
-    """Roll every chroma block of X by get_oti(C1, C2), then csm_fn (cross_recurrence.py:128-134)."""
-    nb = len(C1)
-    per = int(X.shape[1] / nb)
-    oti = get_oti(C1, C2)
-    X1 = np.roll(np.reshape(X, (X.shape[0], per, nb)), oti, axis=2).reshape(X.shape[0], per * nb)
-    return csm_fn(X1, Y)
 
 
 class EarlyFusion(CoverAlgorithm):

@@ -15,25 +15,7 @@ from . import _lib
 from .algorithm_template import CoverAlgorithm
 from .engine import Engine, pack_tracks
 
-__all__ = ["Serra09", "median_sync"]
-
-
-def median_sync(chroma: np.ndarray, fac: int) -> np.ndarray:
-    """``librosa.util.sync(chroma.T, arange(0, n, fac), aggregate=np.median).T`` restated
-    (rqa_serra09.py:51; librosa 0.6.1 pads the boundaries with 0 and n): per-bin median of the
-    blocks [fac*k, min(fac*k+fac, n)), output dtype = input dtype."""
-    chroma = np.asarray(chroma)
-    n = chroma.shape[0]
-    if fac <= 1:
-        return chroma.copy()
-    nblk = (n + fac - 1) // fac
-    out = np.empty((nblk, chroma.shape[1]), dtype=chroma.dtype)
-    full = n // fac
-    if full:
-        out[:full] = np.median(chroma[:full * fac].reshape(full, fac, -1), axis=1)
-    if nblk > full:
-        out[full] = np.median(chroma[full * fac:], axis=0)
-    return out
+__all__ = ["Serra09"]
 
 
 class Serra09(CoverAlgorithm):
@@ -58,7 +40,6 @@ class Serra09(CoverAlgorithm):
         self.tile_pairs = int(tile_pairs)
         self.device = device
         self.crp_path = _lib.CRP_AUTO              # ACOSS_CRP_AUTO (fast path) / ACOSS_CRP_EXACT
-        self.gpu_onramp = True                     # downsample_fac > 1: median aggregation on the GPU
         self.all_feats = {}                      # cached (downsampled) chroma per song
         self._engine = engine
         self._resident = False
@@ -68,10 +49,15 @@ class Serra09(CoverAlgorithm):
 
     # ------------------------------------------------------------------------------------------
     def load_features(self, i):
+        """Downsampled chroma of song i, (n, 12) float32 (rqa_serra09.py:44-53).  With downsample_fac > 1 the
+        per-bin block medians are computed on the GPU for the whole data set at once (acoss_set_tracks_raw) and
+        mirrored into the host cache ``all_feats``; there is no host implementation of the aggregation."""
         if i not in self.all_feats:
-            feats = CoverAlgorithm.load_features(self, i)
-            chroma = np.asarray(feats[self.chroma_type])
-            self.all_feats[i] = median_sync(chroma, self.downsample_fac)
+            if int(self.downsample_fac) > 1:
+                self.engine()                                    # fills all_feats for every song
+            else:
+                feats = CoverAlgorithm.load_features(self, i)
+                self.all_feats[i] = np.array(feats[self.chroma_type])
         return self.all_feats[i]
 
     def params(self, **overrides):
@@ -87,9 +73,11 @@ class Serra09(CoverAlgorithm):
         if self._engine is None:
             self._engine = Engine(self.device)
         if not self._resident:
-            if self.gpu_onramp and 1 < int(self.downsample_fac) <= 128:
+            if int(self.downsample_fac) > 1:
                 # the median aggregation of load_features runs on the GPU (k0_onramp.cu): raw frames go up once,
                 # the downsampled tracks stay resident and are mirrored into the host cache all_feats
+                if int(self.downsample_fac) > 128:
+                    raise ValueError("downsample_fac > 128 is not supported by the GPU on-ramp (acoss_set_tracks_raw)")
                 raws = []
                 for i in range(self.N):
                     feats = CoverAlgorithm.load_features(self, i)         # also fills self.cliques

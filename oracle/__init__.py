@@ -18,6 +18,12 @@ PARITY STATUS
 * EarlyFusion flavour (``earlyfusion_np``): **pinned** against the reference's
   own in-tree code executed in this container (``tests/golden/make_golden.py``
   -> ``tests/golden/*.npz|json``).
+  The full pair scoring (``similarity_pair``, ``get_wcsm``) is pinned by the
+  reference's unmodified ``EarlyFusion.similarity`` method executed here
+  (``tests/golden/make_golden_earlyfusion_full.py``).
 * Evaluation tail (``evalstats_np``): **pinned** against the reference's
   ``CoverAlgorithm.getEvalStatistics`` executed in this container.
+* Feature on-ramp (``onramp_np.median_sync``): **parity unpinned** — restates
+  ``librosa.util.sync(..., aggregate=np.median)`` (librosa is absent from the image),
+  checked against the block-by-block ``np.median`` definition.
 """

@@ -60,8 +60,9 @@ def test_serra09_single_pair_calls(workdir):
 
 def test_serra09_downsample_onramp(workdir):
     """load_features median-downsamples raw HPCP by 40 before upload (rqa_serra09.py:51)."""
-    from acoss_b200.serra09 import Serra09, median_sync
+    from acoss_b200.serra09 import Serra09
     from oracle import serra09_c as oc
+    from oracle.onramp_np import median_sync
     rng = np.random.default_rng(5)
     raw = [rng.random((int(n), 12)).astype(np.float32) for n in (2000, 2400, 1810)]
     s = Serra09(None, None, features=[dict(hpcp=r, label="a") for r in raw])
@@ -154,7 +155,7 @@ def test_gpu_median_onramp_bit_exact():
     """acoss_set_tracks_raw == librosa.util.sync(..., aggregate=np.median) restated by median_sync (np.median on
     float32 blocks): full, short-last and single-frame blocks, odd and even block sizes, ties, several factors."""
     from acoss_b200 import Engine, pack_tracks
-    from acoss_b200.serra09 import median_sync
+    from oracle.onramp_np import median_sync
     rng = np.random.default_rng(12)
     raws = [rng.random((int(n), 12)).astype(np.float32) for n in (2000, 2401, 1810, 41, 40, 39, 1, 81, 517)]
     raws.append(np.round(rng.random((333, 12)) * 4).astype(np.float32) / np.float32(4))       # many ties
@@ -172,17 +173,21 @@ def test_gpu_median_onramp_bit_exact():
 
 
 def test_serra09_gpu_onramp_equals_host_onramp(workdir):
-    """The plugin's GPU on-ramp (default) and the host median give identical scores and cached features."""
-    from acoss_b200.serra09 import Serra09, median_sync
+    """The plugin's GPU on-ramp: load_features (before or after scoring) returns exactly the oracle's block
+    medians, and the scores equal the oracle's on those downsampled tracks."""
+    from acoss_b200.serra09 import Serra09
+    from oracle import serra09_c as oc
+    from oracle.onramp_np import median_sync
     rng = np.random.default_rng(6)
     raw = [rng.random((int(n), 12)).astype(np.float32) for n in (2000, 2400, 1810, 2222)]
     idx = np.array([[0, 1], [0, 2], [1, 2], [2, 3]])
     a = Serra09(None, None, features=[dict(hpcp=r, label="a") for r in raw], shortname="gpuramp")
+    f2 = a.load_features(2)                                   # first touch: the GPU downsamples every song
+    assert f2.dtype == np.float32 and np.array_equal(f2, median_sync(raw[2], 40))
     a.similarity(idx)
-    b = Serra09(None, None, features=[dict(hpcp=r, label="a") for r in raw], shortname="hostramp")
-    b.gpu_onramp = False
-    b.similarity(idx)
-    assert np.array_equal(np.array(a.Ds["main"]), np.array(b.Ds["main"]))
+    ds = [median_sync(r, 40) for r in raw]
+    for i, j in idx:
+        assert a.Ds["main"][i][j] == oc.pair(ds[i], ds[j])
     for i, r in enumerate(raw):
-        assert np.array_equal(a.load_features(i), median_sync(r, 40))
-    a.close(); b.close()
+        assert np.array_equal(a.load_features(i), ds[i])
+    a.close()
