@@ -60,6 +60,7 @@ SIGNATURES = {
     "acoss_debug_counters": (C.c_int, [_vp, _i64p]),
     "acoss_set_profiling": (C.c_int, [_vp, C.c_int]),
     "acoss_stage_ms": (C.c_int, [_vp, _vp]),
+    "acoss_kernel_ms": (C.c_int, [_vp, _vp]),
     "acoss_ef_set_tracks": (C.c_int, [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, _vp, _i64p, C.c_int32, C.c_int32]),
     "acoss_ef_score_pairs": (C.c_int, [_vp, _i32p, C.c_int64, C.c_double, C.c_int32, _fp]),
     "acoss_ef_dump_pair": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, _i32p, _vp, _vp, _fp]),

@@ -55,7 +55,7 @@ struct acoss_ctx {
     size_t ev_used = 0;
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    double stage_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0..3] Serra09 pipeline, [4..8] EarlyFusion pipeline
+    double stage_ms[32] = {0};   // [0..3] Serra09 pipeline, [4..8] EarlyFusion pipeline, [16 + K2K_*] K2 kernels
     // EarlyFusion block features (acoss_ef_set_tracks): float64, row pitch ef_dp[k], kinds mfccs / ssms / chromas
     Buf ef_feat[3], ef_sq[2], ef_cmed, ef_off;
     std::vector<int64_t> ef_hoff;
@@ -80,6 +80,17 @@ struct StageTimer {     // records [a, b] around a pipeline stage when profiling
     }
     void stop() {
         if (c->profiling && a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({stage, a, b}); a = nullptr; }
+    }
+};
+struct CtxKernelTimer : KernelTimer {     // K2 per-kernel spans -> stage_ms[16 + id]; the emit kernel also feeds stage 3
+    acoss_ctx *c; cudaEvent_t a[K2K_COUNT];
+    explicit CtxKernelTimer(acoss_ctx *c_) : c(c_) {}
+    void begin(int id) override { a[id] = get_event(c); cudaEventRecord(a[id], c->stream); }
+    void end(int id) override {
+        cudaEvent_t b = get_event(c);
+        cudaEventRecord(b, c->stream);
+        c->spans.push_back({16 + id, a[id], b});
+        if (id == K2K_EMIT) c->spans.push_back({3, a[id], b});
     }
 };
 static void fold_spans(acoss_ctx *c) {
@@ -419,11 +430,10 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
         ++launches;
         StageTimer t2(c, 1);
         if (fast) {
-            cudaEvent_t ea = nullptr, eb = nullptr;
-            if (c->profiling) { ea = get_event(c); eb = get_event(c); c->spans.push_back({3, ea, eb}); }
+            CtxKernelTimer kt(c);
             TRY(launch_k2_fast(ts, pairs_dev, (const int32_t *)c->oti.p, first, n, *p, g, c->fast.p, fast_slot,
                                (uint32_t *)c->crp.p, (float *)c->thr_q.p, (float *)c->thr_r.p, status, (uint32_t *)c->dbg.p, st, &launches,
-                               ea, eb));
+                               c->profiling ? &kt : nullptr));
             // exact fallback for pairs the fast path flagged: compact their slot ids, re-run in groups
             TRY(ensure(c->fbmap, (size_t)slots * 4 + 64));
             int nfb = 0;
@@ -709,6 +719,15 @@ int acoss_stage_ms(acoss_ctx *c, double ms[4]) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     fold_spans(c);
     for (int i = 0; i < 4; ++i) ms[i] = c->stage_ms[i];
+    return ACOSS_OK;
+}
+
+int acoss_kernel_ms(acoss_ctx *c, double ms[16]) {
+    if (!c || !ms) { acoss_set_error("kernel_ms: NULL argument"); return ACOSS_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fold_spans(c);
+    for (int i = 0; i < 16; ++i) ms[i] = c->stage_ms[16 + i];
     return ACOSS_OK;
 }
 

@@ -61,6 +61,25 @@ __device__ __forceinline__ double acc_f32prod(double acc, float a, float b) {
     return __dadd_rn(acc, (double)__fmul_rn(a, b));
 }
 
+// Optional per-kernel timing hook of the K2 fast path (api.cu records CUDA events on the context stream)
+#define K2K_PREP 0
+#define K2K_SAMPLE 1
+#define K2K_SELECT 2
+#define K2K_HIST_COL 3
+#define K2K_HIST_ROW 4
+#define K2K_HIST_COL2 5
+#define K2K_HIST_ROW2 6
+#define K2K_SPARSE 7
+#define K2K_EMIT 8
+#define K2K_SCATTER 9
+#define K2K_THR 10
+#define K2K_BITS 11
+#define K2K_COUNT 12
+struct KernelTimer {
+    virtual void begin(int id) = 0;
+    virtual void end(int id) = 0;
+};
+
 // host launchers (one per translation unit) -----------------------------------------------------
 struct Params;   // fwd
 

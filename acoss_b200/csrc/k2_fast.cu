@@ -25,6 +25,8 @@
 //    one is flagged and re-run by k2_exact.cu.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "k2_fast.cuh"
 
 namespace {
@@ -39,6 +41,12 @@ constexpr int CAND_CAP = 128;       // candidates per row / column
 constexpr int BRACKET_TARGET = 96;  // a bracket holding more cells than this is split by another histogram level
 constexpr int WPC = 4;              // warps per CTA in the sweep kernels
 constexpr int RCV = 4;              // owned frames per lane (register columns) in the sweep kernels
+#ifndef K2_FFMA2
+#define K2_FFMA2 1                  // 1: packed fma.rn.f32x2 dot products (FFMA2); 0: the same chains as scalar FFMA
+#endif
+#ifndef K2_MINB
+#define K2_MINB 3                   // CTAs per SM the sweep kernels are compiled for (register cap 168 at 3, 255 at 2)
+#endif
 
 struct PairHdr {                    // per-slot header written by fast_prep_kernel
     int32_t nq, nr, Mx, Nx;         // frames and stacked windows of query / reference
@@ -53,8 +61,8 @@ struct PairHdr {                    // per-slot header written by fast_prep_kern
 struct FastLayout {
     size_t slot_bytes;
     size_t off_hdr, off_rrot, off_aaf, off_bbf, off_aai, off_bbi, off_lo, off_w, off_cb, off_sh, off_cnt,
-        off_cand, off_candd, off_rowpack, off_slist, off_scnt, off_samp_r, off_samp_c, off_live, off_nlive;
-    int max_rows, max_cols, max_frames, lines, strips_c, slist_cap;
+        off_cand, off_candz, off_zin, off_zout, off_rowpack, off_pool, off_pcnt, off_samp_r, off_samp_c, off_live, off_nlive;
+    int max_rows, max_cols, max_frames, lines, pool_cap;
     int slog;                           // log2 of the diagonal sampling stride S
     int nst_r, nst_c;                   // sample slots per row (ceil(max_cols / S)) / per column
 };
@@ -79,13 +87,21 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.off_sh = take((size_t)L.lines * 4);
     L.off_cnt = take((size_t)L.lines * 4);
     L.off_cand = take((size_t)L.lines * CAND_CAP * 2);
-    L.off_candd = take((size_t)L.lines * CAND_CAP * 4);
+    L.off_candz = take((size_t)L.lines * CAND_CAP * 4);
+    L.off_zin = take((size_t)L.lines * 4);
+    L.off_zout = take((size_t)L.lines * 4);
     L.off_rowpack = take((size_t)g.max_rows * 16);
-    L.strips_c = (g.max_cols + (32 * RCV - HALO) - 1) / (32 * RCV - HALO);
-    L.slist_cap = 8192;                                   // uncertain cells one emit strip may record
-    while (L.slist_cap < 4 * g.max_rows) L.slist_cap *= 2;
-    L.off_slist = take((size_t)L.strips_c * L.slist_cap * 8);       // 2 words per uncertain cell: i | j << 14, item
-    L.off_scnt = take((size_t)L.strips_c * 4);
+    // uncertain cells of the emit sweep, 8 bytes each (i | j << 14, fixed-point item).  A line contributes its
+    // bracket cells (a few tens whatever its length), so the fraction of uncertain cells falls with the line
+    // length: ~7 % at 500 frames, ~1.7 % at 2k.  Capacity: ~100 cells per line, at most an eighth of the matrix
+    // (more -> the pair takes the exact path)
+    {
+        const int64_t cells = (int64_t)g.max_rows * g.max_cols;
+        const int64_t per_line = (int64_t)100 * (g.max_rows + g.max_cols) / 2;
+        L.pool_cap = (int)std::min<int64_t>(std::max<int64_t>(4096, std::min(per_line, cells / 8)), (int64_t)1 << 26);
+    }
+    L.off_pool = take((size_t)L.pool_cap * 8);
+    L.off_pcnt = take(4);
     // diagonal sampling stride: the bracket a line gets from n_s samples holds ~2.35 L / sqrt(n_s) cells, which
     // the 64-bin split must bring under BRACKET_TARGET  =>  n_s >= (0.003 L)^2, S = L / n_s <= 1 / (9e-6 L)
     {
@@ -115,6 +131,46 @@ __device__ __forceinline__ T *slot_ptr(char *base, const FastLayout &L, int slot
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fixed-point frame-level dot product.  2<x, y> is accumulated by TWO fused-multiply-add chains (even and odd
+// bins, six steps each) that both start at the float magic constant 2^fx_exp, so every partial sum already sits
+// in the fixed-point binade (12 roundings of at most half a unit each: inside the EPS budget).
+// The sum of the raw bits of the two chains is the quantised value + 2 * bits(magic).  The sweep kernels run
+// the two chains as ONE packed sm_100 instruction stream (fma.rn.f32x2, SASS FFMA2: both halves are IEEE fma
+// with round-to-nearest, so they are bit-identical to the scalar chains of dot_fx below, which the sampler, the
+// sparse level and the candidate expansion use).  One side is pre-doubled (exact), so which side it is does
+// not change a bit.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// raw bits of the two half chains, summed (= quantised 2<x, y> + 2 * bits(magic)); x, y: 12 floats each
+__device__ __forceinline__ int dot_fx(const float (&x)[NBINS], const float (&y)[NBINS], float magic) {
+    float ae = magic, ao = magic;
+#pragma unroll
+    for (int b = 0; b < NBINS; b += 2) {
+        ae = __fmaf_rn(x[b], y[b], ae);
+        ao = __fmaf_rn(x[b + 1], y[b + 1], ao);
+    }
+    return __float_as_int(ae) + __float_as_int(ao);
+}
+__device__ __forceinline__ void load_frame(const float *__restrict__ p, float (&x)[NBINS], float scale) {
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    const float4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+    x[0] = scale * v0.x; x[1] = scale * v0.y; x[2] = scale * v0.z; x[3] = scale * v0.w;
+    x[4] = scale * v1.x; x[5] = scale * v1.y; x[6] = scale * v1.z; x[7] = scale * v1.w;
+    x[8] = scale * v2.x; x[9] = scale * v2.y; x[10] = scale * v2.z; x[11] = scale * v2.w;
+}
+
+// ------------------------------------------------------------------------------------------------
 // prep: rotated reference copy, exact float32 norms (reference order) + their fixed-point images,
 // ranks, level-1 histogram range, zeroed candidate counters
 // ------------------------------------------------------------------------------------------------
@@ -138,8 +194,8 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
     }
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     for (int i = threadIdx.x; i < L.lines; i += blockDim.x) cnt[i] = 0u;
-    for (int i = threadIdx.x; i < L.strips_c; i += blockDim.x) slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[i] = 0u;
     if (threadIdx.x < 2) slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive)[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) *slot_ptr<uint32_t>(scratch, L, slot, L.off_pcnt) = 0u;
     __syncthreads();
     float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
     int32_t *aai = slot_ptr<int32_t>(scratch, L, slot, L.off_aai), *bbi = slot_ptr<int32_t>(scratch, L, slot, L.off_bbi);
@@ -233,27 +289,16 @@ __global__ void __launch_bounds__(128) fast_sample_kernel(TrackSet ts, const int
     const int i = i0 + lane;
     const bool iok = lane < SPOS && i < Mx;
     float x[NBINS];
-    {
-        const float4 *p = reinterpret_cast<const float4 *>(Qf + (int64_t)min(i, nq - 1) * NBINS);
-        const float4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
-        x[0] = 2.f * v0.x; x[1] = 2.f * v0.y; x[2] = 2.f * v0.z; x[3] = 2.f * v0.w;
-        x[4] = 2.f * v1.x; x[5] = 2.f * v1.y; x[6] = 2.f * v1.z; x[7] = 2.f * v1.w;
-        x[8] = 2.f * v2.x; x[9] = 2.f * v2.y; x[10] = 2.f * v2.z; x[11] = 2.f * v2.w;
-    }
+    load_frame(Qf + (int64_t)min(i, nq - 1) * NBINS, x, 2.f);
     const int aa = iok ? aai[i] : 0;
-    const int mbits = __float_as_int(magic);
+    const int mbits2 = 2 * __float_as_int(magic);
 #pragma unroll
     for (int kd = 0; kd < SKD; ++kd) {
         const int d = (u0 + kd) << slog;
         const int j = i + d;
-        const float4 *p = reinterpret_cast<const float4 *>(Rf + (int64_t)min(max(j, 0), nr - 1) * NBINS);
-        const float4 y0 = p[0], y1 = p[1], y2 = p[2];
-        float acc = __fmaf_rn(x[0], y0.x, magic);
-        acc = __fmaf_rn(x[1], y0.y, acc); acc = __fmaf_rn(x[2], y0.z, acc); acc = __fmaf_rn(x[3], y0.w, acc);
-        acc = __fmaf_rn(x[4], y1.x, acc); acc = __fmaf_rn(x[5], y1.y, acc); acc = __fmaf_rn(x[6], y1.z, acc);
-        acc = __fmaf_rn(x[7], y1.w, acc); acc = __fmaf_rn(x[8], y2.x, acc); acc = __fmaf_rn(x[9], y2.y, acc);
-        acc = __fmaf_rn(x[10], y2.z, acc); acc = __fmaf_rn(x[11], y2.w, acc);
-        const int v = __float_as_int(acc) - mbits;
+        float yv[NBINS];
+        load_frame(Rf + (int64_t)min(max(j, 0), nr - 1) * NBINS, yv, 1.f);
+        const int v = dot_fx(x, yv, magic) - mbits2;
         const int s1 = v + __shfl_down_sync(0xffffffffu, v, 1);
         const int s2 = s1 + __shfl_down_sync(0xffffffffu, s1, 2);
         const int s4 = s2 + __shfl_down_sync(0xffffffffu, s2, 4);
@@ -346,20 +391,24 @@ __global__ void __launch_bounds__(SEL_THREADS) fast_select_kernel(int n, FastLay
 // ------------------------------------------------------------------------------------------------
 // the sweep: shared by the histogram kernels and the emit kernel
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// the sweep: shared by the histogram kernels and the emit kernel
+// ------------------------------------------------------------------------------------------------
 template <int RC>
 struct Sweep {
     static constexpr int COLS = 32 * RC;          // owned frames per strip
     static constexpr int OUTW = COLS - HALO;      // output windows per strip
-    float y[RC][NBINS];                           // owned frames, pre-doubled
-    int ring[M9][RC];                             // raw bits of the last 9 quantised e values
+    u64 y[RC][NBINS / 2];                         // owned frames, pre-doubled, as (even, odd) bin pairs
+    int ring[M9][RC];                             // raw bits (two magic offsets included) of the last 9 quantised e values
     int T[RC];                                    // fixed-point sliding diagonal sums (of 2e)
     unsigned okm[RC];                             // lane has a left neighbour holding column c-9
     unsigned nz0;                                 // all ones except on lane 0
-    float magic;
-    int mbits;
+    u64 magic2;                                   // (magic, magic)
+    int mbits2;                                   // 2 * bits(magic) (mod 2^32)
 
     __device__ __forceinline__ void init(const float *__restrict__ Y, int nY, int cb, int lane, float magic_) {
-        magic = magic_; mbits = __float_as_int(magic_);
+        magic2 = pack2(magic_, magic_);
+        mbits2 = 2 * __float_as_int(magic_);
         nz0 = lane ? 0xffffffffu : 0u;
 #pragma unroll
         for (int k = 0; k < RC; ++k) {
@@ -367,31 +416,54 @@ struct Sweep {
             const float4 *p = reinterpret_cast<const float4 *>(Y + (int64_t)c * NBINS);
             float4 v0 = make_float4(0, 0, 0, 0), v1 = v0, v2 = v0;
             if (c < nY) { v0 = __ldg(p); v1 = __ldg(p + 1); v2 = __ldg(p + 2); }
-            y[k][0] = 2.f * v0.x; y[k][1] = 2.f * v0.y; y[k][2] = 2.f * v0.z; y[k][3] = 2.f * v0.w;
-            y[k][4] = 2.f * v1.x; y[k][5] = 2.f * v1.y; y[k][6] = 2.f * v1.z; y[k][7] = 2.f * v1.w;
-            y[k][8] = 2.f * v2.x; y[k][9] = 2.f * v2.y; y[k][10] = 2.f * v2.z; y[k][11] = 2.f * v2.w;
+            y[k][0] = pack2(2.f * v0.x, 2.f * v0.y); y[k][1] = pack2(2.f * v0.z, 2.f * v0.w);
+            y[k][2] = pack2(2.f * v1.x, 2.f * v1.y); y[k][3] = pack2(2.f * v1.z, 2.f * v1.w);
+            y[k][4] = pack2(2.f * v2.x, 2.f * v2.y); y[k][5] = pack2(2.f * v2.z, 2.f * v2.w);
             T[k] = 0;
             const int kk = ((k - M9) % RC + RC) % RC;
             okm[k] = (lane >= (M9 - k + kk) / RC) ? 0xffffffffu : 0u;
 #pragma unroll
-            for (int u = 0; u < M9; ++u) ring[u][k] = mbits;
+            for (int u = 0; u < M9; ++u) ring[u][k] = mbits2;
         }
     }
 
-    // frame-level dot products of one streamed frame (12 floats in three float4) with the lane's RC owned
-    // frames, quantised to fixed point (raw float bits of e + magic)
-    __device__ __forceinline__ void dot(const float4 &x0, const float4 &x1, const float4 &x2, int (&eb)[RC]) const {
+    // frame-level dot products of one streamed frame (six (even, odd) pairs) with the lane's RC owned frames
+    __device__ __forceinline__ void dot(const ulonglong2 &x0, const ulonglong2 &x1, const ulonglong2 &x2, int (&eb)[RC]) const {
+#if K2_FFMA2
+        u64 acc[RC];
 #pragma unroll
-        for (int k = 0; k < RC; ++k) {
-            // the chain starts at the magic constant, so every partial sum already sits in the fixed-point
-            // binade (12 roundings of at most half a unit each: inside the EPS budget)
-            float acc = __fmaf_rn(x0.x, y[k][0], magic);
-            acc = __fmaf_rn(x0.y, y[k][1], acc); acc = __fmaf_rn(x0.z, y[k][2], acc); acc = __fmaf_rn(x0.w, y[k][3], acc);
-            acc = __fmaf_rn(x1.x, y[k][4], acc); acc = __fmaf_rn(x1.y, y[k][5], acc); acc = __fmaf_rn(x1.z, y[k][6], acc);
-            acc = __fmaf_rn(x1.w, y[k][7], acc); acc = __fmaf_rn(x2.x, y[k][8], acc); acc = __fmaf_rn(x2.y, y[k][9], acc);
-            acc = __fmaf_rn(x2.z, y[k][10], acc); acc = __fmaf_rn(x2.w, y[k][11], acc);
-            eb[k] = __float_as_int(acc);
+        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x0.x, y[k][0], magic2);
+#pragma unroll
+        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x0.y, y[k][1], acc[k]);
+#pragma unroll
+        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x1.x, y[k][2], acc[k]);
+#pragma unroll
+        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x1.y, y[k][3], acc[k]);
+#pragma unroll
+        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x2.x, y[k][4], acc[k]);
+#pragma unroll
+        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x2.y, y[k][5], acc[k]);
+#pragma unroll
+        for (int k = 0; k < RC; ++k) eb[k] = (int)(unsigned)(acc[k] & 0xffffffffu) + (int)(unsigned)(acc[k] >> 32);
+#else
+        // the same two chains per column as scalar FFMA (bit-identical halves)
+        const u64 xs[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
+        const float mg = __uint_as_float((unsigned)(magic2 & 0xffffffffu));
+        float ae[RC], ao[RC];
+#pragma unroll
+        for (int k = 0; k < RC; ++k) { ae[k] = mg; ao[k] = mg; }
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const float xe = __uint_as_float((unsigned)(xs[b] & 0xffffffffu)), xo = __uint_as_float((unsigned)(xs[b] >> 32));
+#pragma unroll
+            for (int k = 0; k < RC; ++k) {
+                ae[k] = __fmaf_rn(xe, __uint_as_float((unsigned)(y[k][b] & 0xffffffffu)), ae[k]);
+                ao[k] = __fmaf_rn(xo, __uint_as_float((unsigned)(y[k][b] >> 32)), ao[k]);
+            }
         }
+#pragma unroll
+        for (int k = 0; k < RC; ++k) eb[k] = __float_as_int(ae[k]) + __float_as_int(ao[k]);
+#endif
     }
 
     // slides the diagonal sums T by one row.  U = a % 9 (static ring slot).
@@ -404,7 +476,7 @@ struct Sweep {
             const int kk = ((k - M9) % RC + RC) % RC;
             const int dl = (M9 - k + kk) / RC;
             const unsigned v = (unsigned)__shfl_up_sync(0xffffffffu, ring[U][kk], dl);
-            old[k] = (int)((v & okm[k]) | ((unsigned)mbits & ~okm[k]));
+            old[k] = (int)((v & okm[k]) | ((unsigned)mbits2 & ~okm[k]));
         }
         const int tl = (int)((unsigned)__shfl_up_sync(0xffffffffu, T[RC - 1], 1) & nz0);
 #pragma unroll
@@ -425,8 +497,8 @@ template <bool V> struct BC { static constexpr bool value = V; };
 template <int RC, typename PT, typename Fn>
 __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict__ X, const PT *__restrict__ P,
                                           int nrows, Fn &&fn) {
-    const float4 *px = reinterpret_cast<const float4 *>(X);
-    float4 c0 = __ldg(px), c1 = __ldg(px + 1), c2 = __ldg(px + 2);
+    const ulonglong2 *px = reinterpret_cast<const ulonglong2 *>(X);
+    ulonglong2 c0 = __ldg(px), c1 = __ldg(px + 1), c2 = __ldg(px + 2);
     PT pc{};
     const PT *pp = P - HALO;                       // pp[a] is the parameter of row a
     int a = 0;
@@ -515,7 +587,7 @@ __device__ __forceinline__ Bracket split_bracket(const uint32_t *hp, int hs, uin
 // and the next level splits it).
 // ------------------------------------------------------------------------------------------------
 template <int RC, int ORIENT>
-__global__ void __launch_bounds__(32 * WPC, 3) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+__global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
                                                              uint32_t *__restrict__ status, uint32_t *__restrict__ dbg,
@@ -648,20 +720,13 @@ constexpr int SPARSE_LEVELS = 3;
 constexpr int DENSE2_MIN_LIVE = 16;  // live lines a strip must hold for the second dense level to sweep it
 
 template <int U>
-__device__ __forceinline__ void sparse_step(const float (&y)[M9][NBINS], int (&acc)[M9], const float4 &x0, const float4 &x1,
-                                            const float4 &x2, float magic) {
+__device__ __forceinline__ void sparse_step(const float (&y)[M9][NBINS], int (&acc)[M9], const float (&x)[NBINS], float magic) {
 #pragma unroll
     for (int t = 0; t < M9; ++t) {
-        const float *yt = y[t];
-        float a = __fmaf_rn(x0.x, yt[0], magic);
-        a = __fmaf_rn(x0.y, yt[1], a); a = __fmaf_rn(x0.z, yt[2], a); a = __fmaf_rn(x0.w, yt[3], a);
-        a = __fmaf_rn(x1.x, yt[4], a); a = __fmaf_rn(x1.y, yt[5], a); a = __fmaf_rn(x1.z, yt[6], a);
-        a = __fmaf_rn(x1.w, yt[7], a); a = __fmaf_rn(x2.x, yt[8], a); a = __fmaf_rn(x2.y, yt[9], a);
-        a = __fmaf_rn(x2.z, yt[10], a); a = __fmaf_rn(x2.w, yt[11], a);
-        constexpr int dummy = 0; (void)dummy;
+        const int e = dot_fx(x, y[t], magic);
         const int slot = ((U - t) % M9 + M9) % M9;            // row a - t lives in slot (a - t) % 9
-        if (t == 0) acc[slot] = __float_as_int(a);
-        else acc[slot] += __float_as_int(a);
+        if (t == 0) acc[slot] = e;
+        else acc[slot] += e;
     }
 }
 
@@ -701,16 +766,10 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, c
     // owned window j: frames j .. j+8, pre-doubled (the sweeps double the owned side too)
     float y[M9][NBINS];
 #pragma unroll
-    for (int t = 0; t < M9; ++t) {
-        const float4 *p = reinterpret_cast<const float4 *>(Y + (int64_t)min(j + t, nY - 1) * NBINS);
-        const float4 v0 = p[0], v1 = p[1], v2 = p[2];
-        y[t][0] = 2.f * v0.x; y[t][1] = 2.f * v0.y; y[t][2] = 2.f * v0.z; y[t][3] = 2.f * v0.w;
-        y[t][4] = 2.f * v1.x; y[t][5] = 2.f * v1.y; y[t][6] = 2.f * v1.z; y[t][7] = 2.f * v1.w;
-        y[t][8] = 2.f * v2.x; y[t][9] = 2.f * v2.y; y[t][10] = 2.f * v2.z; y[t][11] = 2.f * v2.w;
-    }
+    for (int t = 0; t < M9; ++t) load_frame(Y + (int64_t)min(j + t, nY - 1) * NBINS, y[t], 2.f);
     const int ynj = livel ? yn[j] : 0;
     const int fk = h->fk[side], ck = h->ck[side], rlo = h->lo1, rhi = h->hi1;
-    const int mb9 = M9 * __float_as_int(magic);               // the 9 magic offsets inside a completed sum
+    const int mb9 = 2 * M9 * __float_as_int(magic);           // the 18 magic offsets inside a completed sum (mod 2^32)
     uint32_t *hist = &s_sp[warp][0][lane];
     int lo = livel ? lo_a[j] : 0, sh = livel ? sh_a[j] : 0;
     if (livel && sh < 0) livel = false;
@@ -721,17 +780,18 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, c
 #pragma unroll 1
         for (int b = 0; b < NBIN + 2; ++b) hist[b * 32] = 0u;
         const int yrel = livel ? ynj - lo + (1 << sh) : 0x40000000;   // idle lanes land in the overflow bin
-        const float4 *px = reinterpret_cast<const float4 *>(X);
-        float4 c0 = __ldg(px), c1 = __ldg(px + 1), c2 = __ldg(px + 2);
+        const float *px = X;
+        float xc[NBINS];
+        load_frame(px, xc, 1.f);
         int acc[M9];
 #pragma unroll
         for (int u = 0; u < M9; ++u) acc[u] = 0;
         int a = 0;
         auto step = [&](auto uc) {
             constexpr int U = decltype(uc)::value;
-            sparse_step<U>(y, acc, c0, c1, c2, magic);
-            px += 3;
-            c0 = __ldg(px); c1 = __ldg(px + 1); c2 = __ldg(px + 2);
+            sparse_step<U>(y, acc, xc, magic);
+            px += NBINS;
+            load_frame(px, xc, 1.f);
             if (a >= HALO) {                                  // row a - 8 is complete (slot (U + 1) % 9)
                 const int T = acc[(U + 1) % M9] - mb9;
                 const int zr = __ldg(xn + a - HALO) + yrel - T;
@@ -774,40 +834,78 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, c
 
 // ------------------------------------------------------------------------------------------------
 // emit sweep (orientation 0: owned = reference columns, streamed = query rows)
+//
+// One CTA = WPC adjacent strips of one pair = 480 CRP columns = 15 whole CRP words per row, so the CTA owns
+// its words: plain stores, no atomics on HBM, no zero-filled CRP to start from.  Per cell the sweep
+// classifies: "certainly 1" (one bit shifted into a lane-private accumulator, 4 columns x 8 rows) and
+// "uncertain" (inside a row / column bracket widened by 2 EPS, or near zero).  An uncertain cell's record
+// (i | j << 14, fixed-point item) goes to a lane-private staging column in shared memory with one predicated
+// store.  Every 8 rows the 8 x 8 nibble matrix held by each group of 8 lanes is transposed with three butterfly
+// shuffles (lane p then holds the 32 columns of row 7 - p) and OR-ed into a small shared tile at the strip's bit
+// offset; the staged records are compacted to the pair's pool (one atomic per warp); after one named barrier the
+// CTA's threads store the tile as plain CRP words.
 // ------------------------------------------------------------------------------------------------
+constexpr int EMIT_ROWS = 8;                       // rows per flush block (8 rows x 4 columns = one 32-bit accumulator)
+constexpr int EMIT_TW = 16;                        // tile words per row: word 0 holds only halo bits (always zero)
+constexpr int EMIT_CW = WPC * (32 * RCV - HALO) / 32;   // CRP words a CTA owns per row (15)
+constexpr int EMIT_STAGE = 4 * EMIT_ROWS;           // staged records per lane and flush block: every cell of the block fits
+
+// 8 x 8 nibble transpose across the 8 lanes of a group: out(lane p) nibble q = in(lane q) nibble p
+__device__ __forceinline__ unsigned transpose_nibbles(unsigned x, unsigned selA, unsigned selB, unsigned rotC, unsigned mskC) {
+    unsigned y = __shfl_xor_sync(0xffffffffu, x, 4);
+    x = __byte_perm(x, y, selA);                           // 16-bit halves
+    y = __shfl_xor_sync(0xffffffffu, x, 2);
+    x = __byte_perm(x, y, selB);                           // bytes
+    y = __shfl_xor_sync(0xffffffffu, x, 1);
+    y = __funnelshift_l(y, y, rotC);                       // rotate by +-4 bits, the wrapped nibble is masked off
+    return (x & mskC) | (y & ~mskC);                       // nibbles
+}
+
 template <int RC>
-__global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+__global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
-                                                             char *__restrict__ scratch, int strips_max, float magic,
+                                                             char *__restrict__ scratch, int groups, float magic,
                                                              uint32_t *__restrict__ crp_all, int words,
                                                              int64_t crp_words) {
     using SW = Sweep<RC>;
-    static_assert(RC == 4, "emit word assembly: 4 bits per lane that never straddle a word, groups of <= 8 lanes");
+    static_assert(RC == 4 && WPC == 4 && EMIT_CW * 32 == WPC * SW::OUTW, "a CTA must own whole CRP words");
+    __shared__ uint32_t s_tile[2][EMIT_ROWS][EMIT_TW];        // [buffer][row][word]
+    __shared__ uint2 s_stage[WPC][EMIT_STAGE][32];            // [warp][entry][lane]: lane-private columns, conflict-free
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t task = (int64_t)blockIdx.x * WPC + warp;
-    const int slot = (int)(task / strips_max), strip = (int)(task % strips_max);
+    const int slot = blockIdx.x / groups, grp = blockIdx.x - slot * groups;
     if (slot >= n) return;
     const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
     const int64_t k = first + slot;
     const int q = pairs[2 * k];
     const int nY = h->nr, nX = h->nq, My = nY - M9, Mx = nX - M9;
-    const int cb = strip * SW::OUTW;
-    if (cb >= My) return;
+    uint32_t *crp = crp_all + (int64_t)slot * crp_words;
+    const int w_first = grp * EMIT_CW;                        // first CRP word of this CTA
+    const int cb0 = grp * WPC * SW::OUTW;                     // first CRP column of this CTA
+    const int nact = min(WPC, max(0, (My - cb0 + SW::OUTW - 1) / SW::OUTW));   // strips with columns
+    if (nact == 0) {
+        // nothing to sweep: the CTA's words of the pair's rows are zero (K3 reads the whole row pitch)
+        const int nw = min(words, w_first + EMIT_CW) - w_first;
+        if (nw <= 0) return;
+        for (int e = threadIdx.x; e < Mx * nw; e += blockDim.x) {
+            const int i = e / nw, w = w_first + (e - i * nw);
+            crp[(int64_t)i * words + w] = 0u;
+        }
+        return;
+    }
+    for (int e = threadIdx.x; e < 2 * EMIT_ROWS * EMIT_TW; e += blockDim.x) (&s_tile[0][0][0])[e] = 0u;
+    __syncthreads();
+    if (warp >= nact) return;
+    const int nthr = 32 * nact;
+    const int cb = cb0 + warp * SW::OUTW;
     const float *X = ts.frames + ts.offsets[q] * NBINS;
     const float *Y = slot_ptr<float>(scratch, L, slot, L.off_rrot);
     const int32_t *yn = slot_ptr<int32_t>(scratch, L, slot, L.off_bbi);
     const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
     const int32_t *lo_c = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + L.max_rows;
     const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
-    // list of uncertain cells of this strip: 2 words per cell (i | j << 14, fixed-point item).  Every lane fills
-    // chunks of LCH entries it takes from the strip's pool (one returning atomic per chunk), so an append is a
-    // plain lane-private store: no warp cooperation in the sweep
-    constexpr unsigned LCH = 16;
-    const unsigned lcap = (unsigned)L.slist_cap;
-    uint2 *pool = reinterpret_cast<uint2 *>(slot_ptr<uint32_t>(scratch, L, slot, L.off_slist)) + (size_t)strip * lcap;
-    uint32_t *pool_ctr = slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt) + strip;
-    unsigned lp = 0u, lend = 0u;
-    uint32_t *crp = crp_all + (int64_t)slot * crp_words;
+    uint2 *pool = slot_ptr<uint2>(scratch, L, slot, L.off_pool);
+    uint32_t *pool_ctr = slot_ptr<uint32_t>(scratch, L, slot, L.off_pcnt);
+    const unsigned pool_cap = (unsigned)L.pool_cap;
 
     SW sw;
     sw.init(Y, nY, cb, lane, magic);
@@ -821,25 +919,55 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
         ycl[kk] = valid ? yn[j] - (lo_c[j] - 2 * EPS) : 0x20000000;
         cw1[kk] = valid ? (unsigned)(w_c[j] + 4 * EPS - 1) : 0u;
     }
-    // output placement: strip bit t = RC*lane + kk - HALO <-> CRP column cb + t.  cb is a multiple of 8 and the
-    // lane's RC bits start at a multiple of RC, so they never straddle a 32-bit word: every lane contributes
-    // a nibble to word lword of the row at a position that is constant over the sweep.
-    const unsigned ij0 = (unsigned)(cb + RC * lane - HALO) << 14;   // column part of a list entry (+ kk << 14)
-    const int gpos = (cb & 31) + RC * lane - HALO;
-    const int lword = gpos >> 5;                              // -1 for halo lanes (their columns are invalid: nibble 0)
-    const int lbit = gpos & 31;
-    const unsigned full = 0xffffffffu;
-    // lanes that feed the same CRP word form a group of consecutive lanes; a 3-step segmented OR (shuffle down,
-    // masked by group membership) leaves the complete word in the lowest lane of each group, which owns the store
-    const unsigned gmask = __match_any_sync(full, lword);
-    const bool gleader = (lword >= 0) && ((gmask & ((1u << lane) - 1u)) == 0u);
-    const unsigned m1 = (lane + 1 < 32 && ((gmask >> (lane + 1)) & 1u)) ? 0xffffffffu : 0u;
-    const unsigned m2 = (lane + 2 < 32 && ((gmask >> (lane + 2)) & 1u)) ? 0xffffffffu : 0u;
-    const unsigned m4 = (lane + 4 < 32 && ((gmask >> (lane + 4)) & 1u)) ? 0xffffffffu : 0u;
-    // advances by `words` per row; two rows behind the sweep (segmented-OR pipeline).  Slot 0's rows -2, -1 would
-    // lie before the CRP buffer, but nothing is stored for them (their words are zero)
-    uint32_t *rowp = crp + (cb >> 5) + (lword >= 0 ? lword : 0) - 2 * (int64_t)words;
-    unsigned p1 = 0u, p2 = 0u;
+    // Tile placement.  Strip bit t = RC * lane + kk <-> CRP column cb - HALO + t <-> tile bit 32 + (cb - cb0) - HALO + t
+    // (tile word 0 = the CRP word before the CTA's first one: only halo bits land there, and they are zero).
+    const int tbit0 = 32 + warp * SW::OUTW - HALO;            // tile bit of the strip's first (halo) column
+    const int tw0 = (tbit0 >> 5) + (lane >> 3);               // tile word of this lane's 8-lane group
+    const int toff = tbit0 & 31;                              // 24, 16, 8, 0 for warps 0..3
+    const int grow = 7 - (lane & 7);                          // block row this lane holds after the transpose
+    // transpose constants (lane p of a group: bits 4, 2, 1 of p select the half it keeps)
+    const unsigned selA = (lane & 4) ? 0x3276u : 0x5410u, selB = (lane & 2) ? 0x3715u : 0x6240u;
+    const unsigned rotC = (lane & 1) ? 28u : 4u, mskC = (lane & 1) ? 0xf0f0f0f0u : 0x0f0f0f0fu;
+    const unsigned jcol0 = (unsigned)(cb + RC * lane - HALO) << 14;   // column part of a record (+ kk << 14)
+    unsigned accI = 0u;
+    uint2 *stage = &s_stage[warp][0][lane];
+    unsigned ns = 0u;                                         // staged records of this lane in the current block
+
+    auto flush = [&](int blk) {
+        const unsigned wi = transpose_nibbles(accI, selA, selB, rotC, mskC);
+        accI = 0u;
+        uint32_t *ti = &s_tile[blk & 1][grow][tw0];
+        atomicOr(ti, wi << toff);
+        if (toff) atomicOr(ti + 1, wi >> (32 - toff));
+        // staged uncertain cells -> the pair's pool: exclusive prefix of the lanes' counts, one atomic per warp
+        if (__any_sync(0xffffffffu, ns != 0u)) {
+            const unsigned cnt = ns;
+            unsigned incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            unsigned base = 0u;
+            if (lane == 31) base = atomicAdd(pool_ctr, incl);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+            for (unsigned e = 0; e < cnt; ++e)
+                if (base + e < pool_cap) pool[base + e] = stage[e * 32];
+            ns = 0u;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        // the CTA's threads store the block: 8 rows x 15 words (tile word 0 is not a CRP word of ours)
+#pragma unroll 1
+        for (int e = threadIdx.x; e < EMIT_ROWS * EMIT_TW; e += nthr) {
+            const int g = e >> 4, tw = e & (EMIT_TW - 1);
+            uint32_t *pi = &s_tile[blk & 1][g][tw];
+            const uint32_t vi = *pi;
+            *pi = 0u;                                          // ready for block blk + 2 (one barrier in between)
+            const int i = blk * EMIT_ROWS + g, w = w_first + tw - 1;
+            if (tw >= 1 && i < Mx && w < words) crp[(int64_t)i * words + w] = vi;
+        }
+    };
+
     const int nrows = nX - 1;
     // Per cell, with z the fixed-point item (sign-bit / unsigned-compare arithmetic):
     //   ar = z - (rowLo - 2 EPS), ac = z - (colLo - 2 EPS)
@@ -848,82 +976,56 @@ __global__ void __launch_bounds__(32 * WPC, 3) fast_emit_kernel(TrackSet ts, con
     //   near zero     <=> z < 2 EPS  <=>  ar < 4 EPS - rowLo                 (always evaluated exactly: F7's NaN)
     //   uncertain     <=> row zone or column zone or near zero
     // A near-zero cell that is certainly in is emitted as 1 and listed as well: its exact evaluation either
-    // confirms a tiny distance (<= both thresholds, resolve checks thr against the zone) or raises the NaN error.
+    // confirms a tiny distance or raises the NaN error.
     run_sweep<RC, int4>(sw, X, rowpack, nrows, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
         const int xr = rp.x - rp.y, nz = 2 * EPS - rp.y;
         const unsigned rw1 = (unsigned)(rp.z - 1);
-        int ar[RC];
-        bool unc[RC];
-        unsigned nib = 0u;
+        const int i = a - HALO;                               // CRP row
+        const unsigned rec0 = (unsigned)i | jcol0;
 #pragma unroll
         for (int kk = RC - 1; kk >= 0; --kk) {
-            ar[kk] = xr + ynv[kk] - sw.T[kk];
+            const int ar = xr + ynv[kk] - sw.T[kk];
             const int ac = rp.x + ycl[kk] - sw.T[kk];
-            unc[kk] = ((unsigned)ar[kk] <= rw1) || ((unsigned)ac <= cw1[kk]) || (ar[kk] < nz);
-            nib = __funnelshift_l((unsigned)(ar[kk] & ac), nib, 1);   // sign bit -> bit 0, earlier cells move up
-        }
-        // the three steps of the segmented OR run on three consecutive rows (independent shuffles, no chain):
-        // this row enters step 1, row a-1 step 2, row a-2 step 4 and is stored
-        const unsigned v0 = nib << lbit;
-        const unsigned t1 = __shfl_down_sync(full, v0, 1), t2 = __shfl_down_sync(full, p1, 2),
-                       t4 = __shfl_down_sync(full, p2, 4);
-        const unsigned vout = p2 | (t4 & m4);
-        if (gleader && vout) atomicOr(rowp, vout);            // rows -2, -1 of the pipeline are all zero
-        p2 = p1 | (t2 & m2);
-        p1 = v0 | (t1 & m1);
-        rowp += words;
-        if (__any_sync(full, (unc[0] || unc[1]) || (unc[2] || unc[3]))) {
-            // uncertain cells go to the lane's own list (no warp cooperation); fast_scatter_kernel classifies them
-            const unsigned i = (unsigned)(a - HALO);          // query window (CRP row); i < Mx by construction
-#pragma unroll
-            for (int kk = 0; kk < RC; ++kk) {
-                if (unc[kk]) {
-                    if (lp == lend) { lp = atomicAdd(pool_ctr, LCH); lend = lp + LCH; }
-                    if (lp < lcap) pool[lp] = make_uint2(i | (ij0 + ((unsigned)kk << 14)), (unsigned)(ar[kk] + rp.y));
-                    ++lp;
-                }
+            const bool unc = ((unsigned)ar <= rw1) || ((unsigned)ac <= cw1[kk]) || (ar < nz);
+            accI = __funnelshift_l((unsigned)(ar & ac), accI, 1);   // sign bit -> bit 0, earlier cells move up
+            if (unc) {
+                stage[ns * 32] = make_uint2(rec0 + ((unsigned)kk << 14), (unsigned)(ar + rp.y));
+                ++ns;
             }
         }
+        if ((i & (EMIT_ROWS - 1)) == EMIT_ROWS - 1) flush(i >> 3);
     });
-    (void)Mx;
-    {   // drain the segmented-OR pipeline: rows Mx-2 and Mx-1
-        const unsigned t2 = __shfl_down_sync(full, p1, 2), t4 = __shfl_down_sync(full, p2, 4);
-        const unsigned vout = p2 | (t4 & m4);
-        if (gleader && vout) atomicOr(rowp, vout);
-        p2 = p1 | (t2 & m2);
-        rowp += words;
-        const unsigned t4b = __shfl_down_sync(full, p2, 4);
-        const unsigned vout2 = p2 | (t4b & m4);
-        if (gleader && vout2) atomicOr(rowp, vout2);
+    if (Mx & (EMIT_ROWS - 1)) {                               // last, partial block: missing rows are zero
+        accI <<= 4 * (EMIT_ROWS - (Mx & (EMIT_ROWS - 1)));
+        flush(Mx >> 3);
     }
-    for (; lp < lend; ++lp)                                   // unused tail of the lane's last chunk
-        if (lp < lcap) pool[lp] = make_uint2(0xffffffffu, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
-// scatter: lane lists -> per-row / per-column candidate lists (the returning atomics live here, in a
-// kernel with enough parallelism to hide them)
+// scatter: the pair's pool of uncertain cells -> per-row / per-column candidate lists (index + fixed-point item)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) fast_scatter_kernel(int n, FastLayout L, char *__restrict__ scratch,
+constexpr int SCAT_CHUNK = 4096;    // pool records per CTA
+
+__global__ void __launch_bounds__(256) fast_scatter_kernel(int n, FastLayout L, char *__restrict__ scratch,
                                                            int64_t first, uint32_t *__restrict__ status,
                                                            uint32_t *__restrict__ dbg) {
-    const int slot = blockIdx.y, strip = blockIdx.x;
+    const int slot = blockIdx.y;
     if (slot >= n) return;
-    const uint32_t cntv = slot_ptr<uint32_t>(scratch, L, slot, L.off_scnt)[strip];
-    if (cntv > (uint32_t)L.slist_cap && threadIdx.x == 0) atomicOr(&status[first + slot], PAIR_ST_FALLBACK | 16u);   // reason 16: strip list overflow
-    const uint32_t m = min(cntv, (uint32_t)L.slist_cap);
-    const uint2 *slist = reinterpret_cast<const uint2 *>(slot_ptr<uint32_t>(scratch, L, slot, L.off_slist)) +
-                         (size_t)strip * L.slist_cap;
+    const uint32_t cntv = *slot_ptr<uint32_t>(scratch, L, slot, L.off_pcnt);
+    const uint32_t e0 = blockIdx.x * SCAT_CHUNK;
+    if (e0 >= cntv && blockIdx.x) return;
+    if (cntv > (uint32_t)L.pool_cap && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicOr(&status[first + slot], PAIR_ST_FALLBACK | 16u);          // reason 16: pool overflow
+    const uint32_t m = min(min(cntv, (uint32_t)L.pool_cap), e0 + SCAT_CHUNK);
+    const uint2 *pool = slot_ptr<uint2>(scratch, L, slot, L.off_pool);
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
+    int32_t *candz = slot_ptr<int32_t>(scratch, L, slot, L.off_candz);
     const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
     const int32_t *lo_c = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + L.max_rows;
     const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
-    unsigned total = 0u;
-    for (uint32_t e = threadIdx.x; e < m; e += blockDim.x) {
-        const uint2 rec = slist[e];
-        if (rec.x == 0xffffffffu) continue;                   // unused tail of a lane's chunk
-        ++total;
+    for (uint32_t e = e0 + threadIdx.x; e < m; e += blockDim.x) {
+        const uint2 rec = pool[e];
         const int i = rec.x & 0x3fff, j = (rec.x >> 14) & 0x3fff;
         const int z = (int)rec.y;
         const int4 rp = rowpack[i];                           // {aa_fix, rowLo - 2 EPS, rowW + 4 EPS, -}
@@ -933,21 +1035,25 @@ __global__ void __launch_bounds__(128) fast_scatter_kernel(int n, FastLayout L, 
         const bool cz = ac >= 0 && ac < w_c[j] + 4 * EPS;
         if (rz) {
             const unsigned p = atomicAdd(&cnt[i], 1u);
-            if (p < CAND_CAP) cand[(size_t)i * CAND_CAP + p] = (uint16_t)(j | (ar < 2 * EPS ? 0x8000 : 0));
+            if (p < CAND_CAP) {
+                cand[(size_t)i * CAND_CAP + p] = (uint16_t)(j | (ar < 2 * EPS ? 0x8000 : 0));
+                candz[(size_t)i * CAND_CAP + p] = z;
+            }
         }
         if (cz) {
             const int line = L.max_rows + j;
             const unsigned p = atomicAdd(&cnt[line], 1u);
-            if (p < CAND_CAP) cand[(size_t)line * CAND_CAP + p] = (uint16_t)(i | (ac < 2 * EPS ? 0x8000 : 0));
+            if (p < CAND_CAP) {
+                cand[(size_t)line * CAND_CAP + p] = (uint16_t)(i | (ac < 2 * EPS ? 0x8000 : 0));
+                candz[(size_t)line * CAND_CAP + p] = z;
+            }
         }
     }
-    total = __reduce_add_sync(0xffffffffu, total);
-    const int lane = threadIdx.x & 31;
-    if (lane == 0 && total) atomicAdd(&dbg[24], total);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&dbg[24], min(cntv, (uint32_t)L.pool_cap));
 }
 
 // ------------------------------------------------------------------------------------------------
-// resolve: exact re-evaluation of candidate cells, exact order statistics, thresholds, bit patch
+// resolve: exact order statistics from the candidate lists, thresholds, bit patch
 // ------------------------------------------------------------------------------------------------
 // acc_f32prod with the float -> double widening done on the integer pipe (exact for normal non-negative
 // floats; zero / subnormal products take the conversion instruction).  F2F.F64.F32 issues at 16 lanes/clk/SM
@@ -978,139 +1084,196 @@ __device__ __forceinline__ float exact_item(const float *__restrict__ Q, const f
     return __fadd_rn(__fsub_rn(aa, __fmul_rn(2.f, (float)acc)), bb);
 }
 
-// 32 lines (rows, then columns) per CTA.  Phase 1 walks the CTA's candidates as one flat list, so every thread
-// evaluates the same number of cells whatever the lines' counts are; phase 2 ranks with one 8-lane group per line.
+// Thresholds.  32 lines (rows, then columns) per CTA, 8 lanes per line.  The candidates of a line are ALL its
+// cells with fixed-point item z in the zone [lo - 2 EPS, lo + w + 2 EPS); the histogram levels counted exactly how
+// many cells lie below the zone, so the z-ranks of the wanted order statistics inside the list are known.  Since
+// |z - exact item / unit| <= EPS for every cell, the exact order statistic of rank r differs from the z order
+// statistic zr of the same rank by at most EPS, every cell attaining it has z within 2 EPS of zr, every cell with
+// z < zr - 2 EPS is strictly below it and every cell with z > zr + 2 EPS strictly above.  So only the window
+// cells |z - zr| <= 2 EPS (usually one or two) are evaluated in the reference's exact operation order, and the
+// exact order statistic is the (r - #cells below the window)-th smallest of them.
+constexpr int WIN_CAP = 16;         // window cells per order statistic a line can take; more -> exact path
+constexpr int WFLAT_CAP = 1024;     // window cells of the 32 lines of a CTA
+
 __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                                int64_t first, int n, FastLayout L,
                                                                char *__restrict__ scratch, int guard, double unit,
                                                                float *__restrict__ thr_q_all,
                                                                float *__restrict__ thr_r_all,
-                                                               uint32_t *__restrict__ status) {
-    __shared__ float s_item[32][CAND_CAP];
-    __shared__ float s_sel[32][4];
-    __shared__ int s_pref[33];                                // exclusive prefix of the lines' candidate counts
-    __shared__ int s_nbelow[32];
-    __shared__ int s_nan;
+                                                               uint32_t *__restrict__ status,
+                                                               uint32_t *__restrict__ dbg) {
+    __shared__ int s_z[32][CAND_CAP];
+    __shared__ int s_zsel[32][2];
+    __shared__ float s_win[32][2][WIN_CAP];
+    __shared__ int s_wn[32][2];
+    __shared__ uint32_t s_flat[WFLAT_CAP];                    // cell (i | j << 14) of a window member
+    __shared__ uint16_t s_fdst[WFLAT_CAP][2];                 // its slot in s_win[line][0 / 1] (0xffff: not a member)
+    __shared__ int s_nflat, s_nan;
     const int slot = blockIdx.y;
     if (slot >= n) return;
     const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
-    const int gline0 = blockIdx.x * 32;
-    const int gline = gline0 + grp;                           // 0 .. Mx+Nx-1 (rows then columns)
+    const int gline = blockIdx.x * 32 + grp;                  // 0 .. Mx+Nx-1 (rows then columns)
     const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
     const int Mx = h->Mx, Nx = h->Nx;
+    if (blockIdx.x * 32 >= Mx + Nx) return;
     const bool live = gline < Mx + Nx;
     const bool isrow = gline < Mx;
     const int idx = isrow ? gline : gline - Mx;
     const int line = isrow ? idx : L.max_rows + idx;
     const int64_t k = first + slot;
-    const int q = pairs[2 * k];
-    const float *Q = ts.frames + ts.offsets[q] * NBINS;
-    const float *R = slot_ptr<float>(scratch, L, slot, L.off_rrot);
-    const float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
-    const uint32_t *cnt_a = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
-    const uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand);
-    float *candd = slot_ptr<float>(scratch, L, slot, L.off_candd);
+    const uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand) + (size_t)line * CAND_CAP;
+    const int32_t *candz = slot_ptr<int32_t>(scratch, L, slot, L.off_candz) + (size_t)line * CAND_CAP;
     const unsigned gmask = 0xffu << (8 * ((threadIdx.x & 31) >> 3));
-    if (threadIdx.x < 32) {                                   // warp 0: counts of the CTA's 32 lines and their prefix
-        const int gl = gline0 + threadIdx.x;
-        int c = 0;
-        if (gl < Mx + Nx) c = (int)min(cnt_a[gl < Mx ? gl : L.max_rows + gl - Mx], (unsigned)CAND_CAP);
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)threadIdx.x >= o) incl += v;
-        }
-        s_pref[threadIdx.x + 1] = incl;
-        if (threadIdx.x == 0) { s_pref[0] = 0; s_nan = 0; }
-        s_nbelow[threadIdx.x] = 0;
-    }
-    __syncthreads();
-    const int total = s_pref[32];
-    for (int wi = threadIdx.x; wi < total; wi += 256) {
-        int g = 0;                                            // largest g with s_pref[g] <= wi
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1)
-            if (s_pref[g + o] <= wi) g += o;
-        const int p = wi - s_pref[g];
-        const int gl = gline0 + g;
-        const bool rw = gl < Mx;
-        const int ix = rw ? gl : gl - Mx;
-        const int ln = rw ? ix : L.max_rows + ix;
-        const unsigned e = cand[(size_t)ln * CAND_CAP + p];
-        const int other = e & 0x7fff;
-        const int i = rw ? ix : other, j = rw ? other : ix;
-        const float item = exact_item(Q, R, i, j, aaf[i], bbf[j]);
-        const float d = __fsqrt_rn(item);
-        if (d != d) s_nan = 1;
-        candd[(size_t)ln * CAND_CAP + p] = d;
-        s_item[g][p] = item;
-        if (e >> 15) atomicAdd(&s_nbelow[g], 1);
-    }
-    __syncthreads();
-    int cnt = 0;
+    const int side = isrow ? 0 : 1;
+    int cnt = 0, nbelow = 0;
     bool over = false;
     if (live) {
-        const unsigned c = cnt_a[line];
+        const unsigned c = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt)[line];
         over = c > CAND_CAP;
         cnt = (int)min(c, (unsigned)CAND_CAP);
     }
-    const int nbelow = s_nbelow[grp];
-    const bool nan = (s_nan != 0) && (threadIdx.x == 0);
-    if (!live) return;
-    if (nan) atomicOr(&status[k], PAIR_ST_NAN);
-    const int side = isrow ? 0 : 1;
+    if (sub == 0) { s_wn[grp][0] = 0; s_wn[grp][1] = 0; s_zsel[grp][0] = 0; s_zsel[grp][1] = 0; }
+    if (threadIdx.x == 0) { s_nflat = 0; s_nan = 0; }
+    for (int p = sub; p < cnt; p += 8) {
+        s_z[grp][p] = candz[p];
+        nbelow += cand[p] >> 15;
+    }
+    nbelow += __shfl_xor_sync(gmask, nbelow, 1);
+    nbelow += __shfl_xor_sync(gmask, nbelow, 2);
+    nbelow += __shfl_xor_sync(gmask, nbelow, 4);
+    __syncthreads();
     const int fk = h->fk[side], ck = h->ck[side];
-    const int32_t lo = slot_ptr<int32_t>(scratch, L, slot, L.off_lo)[line];
-    const int32_t w = slot_ptr<int32_t>(scratch, L, slot, L.off_w)[line];
-    const int c0 = slot_ptr<int32_t>(scratch, L, slot, L.off_cb)[line] - nbelow;   // items below every candidate
+    const bool quirk = h->quirk[side] != 0;
+    const int32_t lo = live ? slot_ptr<int32_t>(scratch, L, slot, L.off_lo)[line] : 0;
+    const int32_t w = live ? slot_ptr<int32_t>(scratch, L, slot, L.off_w)[line] : 0;
+    const int c0 = live ? slot_ptr<int32_t>(scratch, L, slot, L.off_cb)[line] - nbelow : 0;   // cells below every candidate
     const int rfk = fk - c0, rck = ck - c0;
     unsigned bad = over ? 32u : 0u;                           // reason 32: more than CAND_CAP candidates on a line
-    float thr = 0.f;
-    if (!h->quirk[side]) {
-        if (rfk < 0 || rck >= cnt || rfk > rck) bad |= 64u;   // reason 64: ranks not inside the candidate set
-        // rank by counting (cnt <= 32): the candidate whose rank is rfk / rck publishes its item
+    const bool sel = live && !quirk;
+    if (sel && (rfk < 0 || rck >= cnt || rfk > rck)) bad |= 64u;   // reason 64: ranks not inside the candidate set
+    // z order statistics of ranks rfk, rck by counting (ties broken by list position)
+    if (sel && !bad) {
         for (int p = sub; p < cnt; p += 8) {
-            const float v = s_item[grp][p];
+            const int v = s_z[grp][p];
             int rank = 0;
             for (int p2 = 0; p2 < cnt; ++p2) {
-                const float v2 = s_item[grp][p2];
+                const int v2 = s_z[grp][p2];
                 rank += (v2 < v) || (v2 == v && p2 < p);
             }
-            if (rank == rfk) s_sel[grp][0] = v;
-            if (rank == rck) s_sel[grp][1] = v;
+            if (rank == rfk) s_zsel[grp][0] = v;
+            if (rank == rck) s_zsel[grp][1] = v;
         }
-        __syncwarp(gmask);
-        if (!bad) {
-            const float ifk = s_sel[grp][0], ick = s_sel[grp][1];
-            // every excluded cell below the candidate zone has exact item < (lo - EPS) units, every excluded cell
-            // above it has exact item >= (lo + w + EPS) units: the selected order statistics must sit between
-            const double lo_e = (double)(lo - EPS) * unit, hi_e = (double)(lo + w + EPS) * unit;
-            if ((double)ifk < lo_e || (double)ick >= hi_e) bad |= 128u;   // reason 128: order statistic outside its zone
+    }
+    __syncwarp(gmask);
+    const int zf = s_zsel[grp][0], zc = s_zsel[grp][1];
+    // window cells go to the CTA's flat list (evaluated below by all threads: no divergence on the long exact
+    // evaluation); cells below each window are counted
+    int nbf = 0, nbc = 0;
+    if (sel && !bad) {
+        for (int p = sub; p < cnt; p += 8) {
+            const int v = s_z[grp][p];
+            nbf += (v < zf - 2 * EPS) ? 1 : 0;
+            nbc += (v < zc - 2 * EPS) ? 1 : 0;
+            const bool inf = (v >= zf - 2 * EPS) && (v <= zf + 2 * EPS), inc = (v >= zc - 2 * EPS) && (v <= zc + 2 * EPS);
+            if (inf || inc) {
+                const int other = cand[p] & 0x7fff;
+                const int i = isrow ? idx : other, j = isrow ? other : idx;
+                const int sf = inf ? atomicAdd(&s_wn[grp][0], 1) : WIN_CAP, sc = inc ? atomicAdd(&s_wn[grp][1], 1) : WIN_CAP;
+                const int e = atomicAdd(&s_nflat, 1);
+                if (e < WFLAT_CAP) {
+                    s_flat[e] = (uint32_t)i | ((uint32_t)j << 14);
+                    s_fdst[e][0] = (uint16_t)(sf < WIN_CAP ? grp * WIN_CAP + sf : 0xffff);
+                    s_fdst[e][1] = (uint16_t)(sc < WIN_CAP ? grp * WIN_CAP + sc : 0xffff);
+                }
+            }
+        }
+    }
+    nbf += __shfl_xor_sync(gmask, nbf, 1); nbf += __shfl_xor_sync(gmask, nbf, 2); nbf += __shfl_xor_sync(gmask, nbf, 4);
+    nbc += __shfl_xor_sync(gmask, nbc, 1); nbc += __shfl_xor_sync(gmask, nbc, 2); nbc += __shfl_xor_sync(gmask, nbc, 4);
+    __syncthreads();
+    {
+        const int nflat = min(s_nflat, WFLAT_CAP);
+        const int q = pairs[2 * k];
+        const float *Q = ts.frames + ts.offsets[q] * NBINS;
+        const float *R = slot_ptr<float>(scratch, L, slot, L.off_rrot);
+        const float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
+        for (int e = threadIdx.x; e < nflat; e += blockDim.x) {
+            const uint32_t cell = s_flat[e];
+            const int i = cell & 0x3fff, j = cell >> 14;
+            const float item = exact_item(Q, R, i, j, aaf[i], bbf[j]);
+            if (item != item || item < 0.f) s_nan = 1;        // sqrtf of a negative item is the reference's NaN (F7)
+            const unsigned d0 = s_fdst[e][0], d1 = s_fdst[e][1];
+            if (d0 != 0xffffu) s_win[d0 / WIN_CAP][0][d0 % WIN_CAP] = item;
+            if (d1 != 0xffffu) s_win[d1 / WIN_CAP][1][d1 % WIN_CAP] = item;
+        }
+        if (threadIdx.x == 0 && nflat) atomicAdd(&dbg[25], (unsigned)nflat);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_nan) atomicOr(&status[k], PAIR_ST_NAN);
+        if (s_nflat > WFLAT_CAP) atomicOr(&status[k], PAIR_ST_FALLBACK | 128u);
+    }
+    if (!live || sub != 0) return;
+    float thr = 0.f;
+    int zin = -0x40000000, zout = -0x40000000;                // thr = 0 (F1 quirk): only an exact zero distance is in, and near-zero cells are always evaluated exactly
+    if (sel && !bad) {
+        const int nf = s_wn[grp][0], nc = s_wn[grp][1];
+        const int wf = rfk - nbf, wc = rck - nbc;             // ranks inside the windows
+        if (nf > WIN_CAP || nc > WIN_CAP) bad |= 128u;        // reason 128: too many cells within 2 EPS of an order statistic
+        else if (wf < 0 || wf >= nf || wc < 0 || wc >= nc) bad |= 256u;   // reason 256: window rank inconsistent
+        else {
+            float ifk = 0.f, ick = 0.f;
+            for (int a = 0; a < nf; ++a) {
+                const float v = s_win[grp][0][a];
+                int rank = 0;
+                for (int b = 0; b < nf; ++b) { const float v2 = s_win[grp][0][b]; rank += (v2 < v) || (v2 == v && b < a); }
+                if (rank == wf) ifk = v;
+            }
+            for (int a = 0; a < nc; ++a) {
+                const float v = s_win[grp][1][a];
+                int rank = 0;
+                for (int b = 0; b < nc; ++b) { const float v2 = s_win[grp][1][b]; rank += (v2 < v) || (v2 == v && b < a); }
+                if (rank == wc) ick = v;
+            }
+            // the a-priori bound |z - item / unit| <= EPS, checked on the selected cells (with margin)
+            if (fabs((double)ifk / unit - (double)zf) > (double)(2 * EPS) || fabs((double)ick / unit - (double)zc) > (double)(2 * EPS))
+                bad |= 512u;                                  // reason 512: fixed-point bound violated
             const float sfk = __fsqrt_rn(ifk), sck = __fsqrt_rn(ick);
             const float kf = h->kf[side];
             const float fkf = floorf(kf), ckf = ceilf(kf);
             if (guard && fkf == ckf) thr = sfk;
             else thr = __fadd_rn(__fmul_rn(sfk, __fsub_rn(ckf, kf)), __fmul_rn(sck, __fsub_rn(kf, fkf)));
-            // cells emitted as certainly-in have exact item < (lo - EPS): their d must be <= thr;
-            // cells dropped as certainly-out have exact item >= (lo + w + EPS): their d must be > thr
+            // integer bounds for the bit decisions of resolve_bits: with t2 = thr^2 (exact in double),
+            //   item <= t2                => sqrtf(item) <= thr           (sqrt and rounding are monotonic)
+            //   item >  t2 (1 + 2^-21)    => sqrtf(item) >= nextafter(thr) > thr
+            // and |z - item / unit| <= EPS
             const double t2 = (double)thr * (double)thr;
-            if (lo_e > 0.0 && t2 < lo_e * (1.0 + 1e-6)) bad |= 256u;   // reason 256/512: threshold not between the certain sets
-            if (t2 >= hi_e * (1.0 - 1e-6)) bad |= 512u;
+            const double zi = floor(t2 / unit) - (double)EPS - 1.0, zo = ceil(t2 * (1.0 + 4.76837158203125e-07) / unit) + (double)EPS + 1.0;
+            zin = (int)fmax(fmin(zi, 1.0e9), -1.0e9);
+            zout = (int)fmax(fmin(zo, 1.0e9), -1.0e9);
+            // every cell the sweep emitted as certainly-in has z < lo - 2 EPS, every cell it dropped has z >= lo + w + 2 EPS
+            if (zin < lo - 2 * EPS - 1 || zout > lo + w + 2 * EPS) bad |= 1024u;   // reason 1024: threshold not between the certain sets
         }
     }
-    if (sub == 0) {
-        if (bad) atomicOr(&status[k], PAIR_ST_FALLBACK | bad);
-        if (isrow) thr_q_all[(int64_t)slot * L.max_rows + idx] = thr;
-        else thr_r_all[(int64_t)slot * L.max_cols + idx] = thr;
-    }
+    if (bad) atomicOr(&status[k], PAIR_ST_FALLBACK | bad);
+    if (isrow) thr_q_all[(int64_t)slot * L.max_rows + idx] = thr;
+    else thr_r_all[(int64_t)slot * L.max_cols + idx] = thr;
+    slot_ptr<int32_t>(scratch, L, slot, L.off_zin)[line] = zin;
+    slot_ptr<int32_t>(scratch, L, slot, L.off_zout)[line] = zout;
 }
 
-__global__ void __launch_bounds__(256) fast_resolve_bits_kernel(int n, FastLayout L, char *__restrict__ scratch,
+// Bits of the listed (uncertain) cells.  A cell is 1 iff thrQ[i] - d >= 0 and thrR[j] - d >= 0.  Each side is decided
+// from z and the line's integer bounds when that is certain (z <= zin: in, z >= zout: out); the few cells in between
+// (and every near-zero cell, for the NaN rule F7) are evaluated exactly.  A cell listed by its row and its column is
+// handled from the row list only.
+__global__ void __launch_bounds__(256) fast_resolve_bits_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+                                                                int64_t first, int n, FastLayout L,
+                                                                char *__restrict__ scratch,
                                                                 const float *__restrict__ thr_q_all,
                                                                 const float *__restrict__ thr_r_all,
                                                                 uint32_t *__restrict__ crp_all, int words,
-                                                                int64_t crp_words) {
+                                                                int64_t crp_words, uint32_t *__restrict__ status,
+                                                                uint32_t *__restrict__ dbg) {
     const int slot = blockIdx.y;
     if (slot >= n) return;
     const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
@@ -1122,14 +1285,41 @@ __global__ void __launch_bounds__(256) fast_resolve_bits_kernel(int n, FastLayou
     const int idx = isrow ? gline : gline - Mx;
     const int line = isrow ? idx : L.max_rows + idx;
     const int cnt = (int)min(slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt)[line], (uint32_t)CAND_CAP);
+    if (cnt == 0) return;
+    const int64_t k = first + slot;
+    const uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand) + (size_t)line * CAND_CAP;
+    const int32_t *candz = slot_ptr<int32_t>(scratch, L, slot, L.off_candz) + (size_t)line * CAND_CAP;
+    const int32_t *zin = slot_ptr<int32_t>(scratch, L, slot, L.off_zin), *zout = slot_ptr<int32_t>(scratch, L, slot, L.off_zout);
+    const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
     for (int p = sub; p < cnt; p += 16) {
-    const unsigned e = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand)[(size_t)line * CAND_CAP + p];
-    const float d = slot_ptr<float>(scratch, L, slot, L.off_candd)[(size_t)line * CAND_CAP + p];
-    const int other = e & 0x7fff;
-    const int i = isrow ? idx : other, j = isrow ? other : idx;
-    const float tq = thr_q_all[(int64_t)slot * L.max_rows + i], tr = thr_r_all[(int64_t)slot * L.max_cols + j];
-    if ((__fsub_rn(tq, d) >= 0.f) && (__fsub_rn(tr, d) >= 0.f))
-        atomicOr(crp_all + (int64_t)slot * crp_words + (int64_t)i * words + (j >> 5), 1u << (j & 31));
+        const int other = cand[p] & 0x7fff;
+        const int z = candz[p];
+        const int i = isrow ? idx : other, j = isrow ? other : idx;
+        const bool zz = z < 2 * EPS;
+        if (!isrow) {                                         // also on the row's list? then the row handles it
+            const int4 rp = rowpack[i];
+            const int ar = z - rp.y;
+            if ((ar >= 0 && ar < rp.z) || zz) continue;
+        }
+        const int lr = i, lc = L.max_rows + j;
+        const int zir = zin[lr], zor = zout[lr], zic = zin[lc], zoc = zout[lc];
+        const bool in_r = z <= zir, out_r = z >= zor, in_c = z <= zic, out_c = z >= zoc;
+        bool one;
+        if (!zz && (out_r || out_c)) continue;
+        if (!zz && in_r && in_c) one = true;
+        else {
+            const int q = pairs[2 * k];
+            const float *Q = ts.frames + ts.offsets[q] * NBINS;
+            const float *R = slot_ptr<float>(scratch, L, slot, L.off_rrot);
+            const float item = exact_item(Q, R, i, j, slot_ptr<float>(scratch, L, slot, L.off_aaf)[i],
+                                          slot_ptr<float>(scratch, L, slot, L.off_bbf)[j]);
+            const float d = __fsqrt_rn(item);
+            if (d != d) atomicOr(&status[k], PAIR_ST_NAN);
+            const float tq = thr_q_all[(int64_t)slot * L.max_rows + i], tr = thr_r_all[(int64_t)slot * L.max_cols + j];
+            one = (__fsub_rn(tq, d) >= 0.f) && (__fsub_rn(tr, d) >= 0.f);
+            atomicAdd(&dbg[25], 1u);
+        }
+        if (one) atomicOr(crp_all + (int64_t)slot * crp_words + (int64_t)i * words + (j >> 5), 1u << (j & 31));
     }
 }
 
@@ -1155,7 +1345,7 @@ size_t k2_fast_slot_bytes(const SlotGeom &g, int max_frames) { return make_layou
 int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti, int64_t first, int n,
                    const acoss_params &p, const SlotGeom &g, void *scratch, size_t slot_bytes, uint32_t *crp,
                    float *thr_q, float *thr_r, uint32_t *status, uint32_t *dbg, cudaStream_t st, int64_t *launches,
-                   cudaEvent_t emit_begin, cudaEvent_t emit_end) {
+                   KernelTimer *timer) {
     if (n <= 0) return ACOSS_OK;
     constexpr int RC = RCV;
     const FastLayout L = make_layout(g, ts.max_frames);
@@ -1166,9 +1356,12 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     const float magic = ldexpf(1.f, ts.fx_exp);
     const double unit = ldexp(1.0, ts.fx_exp - 23);
     const float fx_scale = ldexpf(1.f, 23 - ts.fx_exp);
-    CUDA_TRY(cudaMemsetAsync(crp, 0, (size_t)n * g.crp_words * 4, st));
+    auto tb = [&](int id) { if (timer) timer->begin(id); };
+    auto te = [&](int id) { if (timer) timer->end(id); };
+    tb(K2K_PREP);
     fast_prep_kernel<<<n, 256, 0, st>>>(ts, pairs, oti, first, L, base, qperc, p.integer_guard, fx_scale);
     CUDA_TRY(cudaGetLastError());
+    te(K2K_PREP);
     const int outw = Sweep<RC>::OUTW;
     const int strips_c = (g.max_cols + outw - 1) / outw, strips_r = (g.max_rows + outw - 1) / outw;
     const size_t smem = (size_t)WPC * (NBIN + 2) * (RC / 2) * 32 * 4;
@@ -1192,38 +1385,62 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
         const int nu_max = ((g.max_rows - 1) >> L.slog) + ((g.max_cols - 1) >> L.slog) + 1;
         const int ngrp = (nu_max + SKD - 1) / SKD, nblk = (g.max_rows + SPOS - 1) / SPOS;
         const int64_t warps = (int64_t)n * ngrp * nblk;
+        tb(K2K_SAMPLE);
         fast_sample_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(ts, pairs, first, n, L, base, ngrp, nblk, magic);
         CUDA_TRY(cudaGetLastError());
+        te(K2K_SAMPLE);
+        tb(K2K_SELECT);
         fast_select_kernel<<<dim3((lines + SEL_THREADS - 1) / SEL_THREADS, n), SEL_THREADS, smem_sel, st>>>(n, L, base);
         CUDA_TRY(cudaGetLastError());
+        te(K2K_SELECT);
     }
     // two dense levels per orientation: the second sweeps only strips that still hold DENSE2_MIN_LIVE or more live
     // lines (short lines start from the whole item range and need it; ordinary strips skip it at once) and hands
     // every line still live to the sparse refinement
+    tb(K2K_HIST_COL);
     fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg, 1, 0);
+    te(K2K_HIST_COL);
+    tb(K2K_HIST_ROW);
     fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 4, 1, 0);
+    te(K2K_HIST_ROW);
+    tb(K2K_HIST_COL2);
     fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1);
+    te(K2K_HIST_COL2);
+    tb(K2K_HIST_ROW2);
     fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1);
     CUDA_TRY(cudaGetLastError());
+    te(K2K_HIST_ROW2);
     {
         const int64_t warps = (int64_t)n * 2 * (SPARSE_CAP / 32);
+        tb(K2K_SPARSE);
         fast_sparse_kernel<<<(unsigned)((warps + WPC - 1) / WPC), 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, magic, status, dbg + 8);
         CUDA_TRY(cudaGetLastError());
+        te(K2K_SPARSE);
     }
-    if (emit_begin) CUDA_TRY(cudaEventRecord(emit_begin, st));
-    // 3 CTAs / SM (168 registers): 4 CTAs (128 registers, spills) measured 3 % slower
-    fast_emit_kernel<RC><<<gc, 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, strips_c, magic, crp, g.words, g.crp_words);
+    {
+        // one CTA per group of WPC strips (EMIT_CW whole CRP words per row); the groups also cover the row pitch padding
+        const int groups = std::max((strips_c + WPC - 1) / WPC, (g.words + EMIT_CW - 1) / EMIT_CW);
+        tb(K2K_EMIT);
+        fast_emit_kernel<RC><<<(unsigned)((int64_t)n * groups), 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, groups, magic, crp,
+                                                                                g.words, g.crp_words);
+        CUDA_TRY(cudaGetLastError());
+        te(K2K_EMIT);
+    }
+    tb(K2K_SCATTER);
+    fast_scatter_kernel<<<dim3((L.pool_cap + SCAT_CHUNK - 1) / SCAT_CHUNK, n), 256, 0, st>>>(n, L, base, first, status, dbg);
     CUDA_TRY(cudaGetLastError());
-    if (emit_end) CUDA_TRY(cudaEventRecord(emit_end, st));
-    fast_scatter_kernel<<<dim3(strips_c, n), 128, 0, st>>>(n, L, base, first, status, dbg);
-    CUDA_TRY(cudaGetLastError());
+    te(K2K_SCATTER);
+    tb(K2K_THR);
     fast_resolve_thr_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(ts, pairs, first, n, L, base, p.integer_guard, unit,
-                                                                       thr_q, thr_r, status);
+                                                                       thr_q, thr_r, status, dbg);
     CUDA_TRY(cudaGetLastError());
-    fast_resolve_bits_kernel<<<dim3((lines * 16 + 255) / 256, n), 256, 0, st>>>(n, L, base, thr_q, thr_r, crp, g.words,
-                                                                                      g.crp_words);
+    te(K2K_THR);
+    tb(K2K_BITS);
+    fast_resolve_bits_kernel<<<dim3((lines * 16 + 255) / 256, n), 256, 0, st>>>(ts, pairs, first, n, L, base, thr_q, thr_r, crp,
+                                                                                      g.words, g.crp_words, status, dbg);
     CUDA_TRY(cudaGetLastError());
-    if (launches) *launches += 16;
+    te(K2K_BITS);
+    if (launches) *launches += 15;
     return ACOSS_OK;
 }
 

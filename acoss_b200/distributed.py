@@ -85,16 +85,42 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None):
     if rows not in (1, len(keys)):
         raise ValueError("score rows (%d) do not match the score types %r" % (rows, keys))
     backend = dist.get_backend() if dist.is_initialized() else "none"
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    # staging device: the plugin's own device (alg.device), not whatever torch's current device happens to be —
+    # with one process per GPU every rank must stage on ITS GPU or NCCL deadlocks
+    if backend == "nccl":
+        dev = torch.device("cuda", int(getattr(alg, "device", torch.cuda.current_device())))
+        torch.cuda.set_device(dev)
+    else:
+        dev = torch.device("cpu")
     # one gather for all score rows: rank r contributes rows x (bounds[r+1] - bounds[r]) floats, row-major
     flat = np.ascontiguousarray(local.reshape(rows, -1)).ravel()
-    full = gather_scores(torch.from_numpy(flat).to(dev), bounds * rows, rank, world).cpu().numpy()
-    per_key = np.empty((rows, len(pairs)), dtype=np.float32)
-    for r in range(world):
-        a, b = int(bounds[r]), int(bounds[r + 1])
-        per_key[:, a:b] = full[a * rows:b * rows].reshape(rows, b - a)
-    for k, key in enumerate(keys):
-        alg.Ds[key][pairs[:, 0], pairs[:, 1]] = per_key[k if rows > 1 else 0]
-        if symmetric:
-            alg.Ds[key] += alg.Ds[key].T
+    full = gather_scores(torch.from_numpy(flat).to(dev), bounds * rows, rank, world)
+    fill_score_matrices(alg, pairs, full, bounds, rows, keys, symmetric, world)
     return bounds
+
+
+def fill_score_matrices(alg, pairs, full, bounds, rows, keys, symmetric, world):
+    """Gathered score vector -> alg.Ds[key].  The (N, N) matrix is assembled in a PRIVATE buffer — on the
+    staging device when that is a GPU (one index_put_ + one transposed add, then ONE contiguous device-to-host
+    copy), in a private ndarray otherwise — and then written to alg.Ds[key] by a plain, idempotent assignment.
+    Ranks of one box that were constructed with the same cache prefix map the same memmap file: an in-place
+    `Ds += Ds.T` on the shared file would symmetrise twice (scores doubled); a plain assignment of the finished
+    matrix cannot."""
+    import torch
+    N = int(alg.N)
+    # rank r's slice holds its rows back to back (row-major rows x n_r): un-interleave into (rows, n_pairs)
+    if rows == 1:
+        per_key = full.reshape(1, -1)
+    else:
+        per_key = torch.empty((rows, len(pairs)), dtype=torch.float32, device=full.device)
+        for r in range(world):
+            a, b = int(bounds[r]), int(bounds[r + 1])
+            per_key[:, a:b] = full[a * rows:b * rows].reshape(rows, b - a)
+    pi = torch.from_numpy(np.ascontiguousarray(pairs[:, 0]).astype(np.int64)).to(full.device)
+    pj = torch.from_numpy(np.ascontiguousarray(pairs[:, 1]).astype(np.int64)).to(full.device)
+    for k, key in enumerate(keys):
+        D = torch.zeros((N, N), dtype=torch.float32, device=full.device)
+        D.index_put_((pi, pj), per_key[k if rows > 1 else 0])
+        if symmetric:
+            D = D + D.T                                    # out of place: no aliasing between D and its transpose
+        alg.Ds[key][:, :] = D.cpu().numpy()

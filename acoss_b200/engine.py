@@ -197,6 +197,15 @@ class Engine:
         check(self._lib.acoss_stage_ms(self._ctx, ms.ctypes.data))
         return dict(k1_oti=float(ms[0]), k2_crp=float(ms[1]), k3_dp=float(ms[2]), k2_emit=float(ms[3]))
 
+    K2_KERNELS = ("prep", "sample", "select", "hist_col", "hist_row", "hist_col2", "hist_row2", "sparse", "emit",
+                  "scatter", "thr", "bits")
+
+    def kernel_ms(self) -> dict:
+        """Accumulated CUDA-event milliseconds of every kernel of the fast K2 path since set_profiling(True)."""
+        ms = np.zeros(16, dtype=np.float64)
+        check(self._lib.acoss_kernel_ms(self._ctx, ms.ctypes.data))
+        return {k: float(ms[i]) for i, k in enumerate(self.K2_KERNELS)}
+
     def debug_counters(self) -> dict:
         """Diagnostic counters of the last scoring call (acoss_debug_counters): dense histogram level per
         orientation (strips, live lines, bracket misses, lines left), sparse refinement (warps, sweeps,

@@ -38,6 +38,49 @@ def _worker(rank, world, port, tmp, q):
     dist.destroy_process_group()
 
 
+def _worker_shared(rank, world, port, tmp, q):
+    """Every rank constructs the plugin with the SAME cache prefix: all ranks map the same memmap file."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    os.chdir(tmp)
+    import torch.distributed as dist
+    from acoss_b200.distributed import all_pairwise_distributed
+    from acoss_b200.serra09 import Serra09
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    feats = [dict(hpcp=rng.random((int(n), 12)).astype(np.float32), label=str(i // 3))
+             for i, n in enumerate(rng.integers(20, 200, size=17))]
+    alg = Serra09(None, None, features=feats, downsample_fac=1, shortname="shared", cachedir="cache_shared")
+    dist.barrier()                                          # every constructor has truncated the file by now
+    all_pairwise_distributed(alg, symmetric=True, score_fn=_fake_score)
+    dist.barrier()                                          # every rank has written
+    q.put((rank, np.array(alg.Ds["main"])))
+    dist.destroy_process_group()
+
+
+def test_distributed_shared_cache_prefix_is_not_doubled(tmp_path):
+    """ranks that share one memmap file must not symmetrise it twice (plain idempotent assignment)."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_shared, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 17
+    i, j = np.triu_indices(n, k=1)
+    want = np.zeros((n, n), np.float32)
+    want[i, j] = _fake_score(np.stack([i, j], 1))
+    want = want + want.T
+    for rank, D in res:
+        assert np.array_equal(D, want)
+
+
 def _fake_score4(pairs):
     p = np.asarray(pairs, dtype=np.int64)
     base = ((p[:, 0] * 37 + p[:, 1] * 11) % 500).astype(np.float32)
