@@ -29,7 +29,9 @@ class Params(C.Structure):
     """Mirror of ``acoss_params`` (include/acoss_b200.h)."""
     _fields_ = [("m", C.c_int32), ("tau", C.c_int32), ("kappa", C.c_float), ("oti", C.c_int32),
                 ("noti", C.c_int32), ("gamma_o", C.c_float), ("gamma_e", C.c_float),
-                ("align", C.c_int32), ("integer_guard", C.c_int32), ("crp_path", C.c_int32)]
+                ("align", C.c_int32), ("integer_guard", C.c_int32), ("crp_path", C.c_int32),
+                ("f2_strict", C.c_int32), ("f3_float_acc", C.c_int32), ("f4_keep_last", C.c_int32),
+                ("f5_asymmetric", C.c_int32)]
 
 
 _lib = None

@@ -132,7 +132,11 @@ void acoss_default_params(acoss_params *p) {
     p->m = 9; p->tau = 1; p->kappa = 0.095f; p->oti = 1; p->noti = 12;
     p->gamma_o = 0.5f; p->gamma_e = 0.5f; p->align = ACOSS_ALIGN_QMAX; p->integer_guard = 0;
     p->crp_path = ACOSS_CRP_AUTO;
+    p->f2_strict = 0; p->f3_float_acc = 0; p->f4_keep_last = 0; p->f5_asymmetric = 0;
 }
+
+// stacked frames of a track with n frames: n - win_incr (F4: essentia drops one window)
+static int win_incr(const acoss_params *p) { return p->f4_keep_last ? (p->m - 1) * p->tau : p->m * p->tau; }
 
 const char *acoss_last_error(void) { return g_err; }
 const char *acoss_version(void) { return "acoss_b200 0.1 (sm_100a)"; }
@@ -334,7 +338,7 @@ static int check_params(const acoss_ctx *c, const acoss_params *p) {
         acoss_set_error("align mode %d not implemented for the pair pipeline", p->align);
         return ACOSS_E_INVALID;
     }
-    const int incr = p->m * p->tau;
+    const int incr = win_incr(p);
     if (c->min_frames < incr + 2) {
         acoss_set_error("a track has %d frames; essentia needs at least m*tau+2 = %d (F9)", c->min_frames, incr + 2);
         return ACOSS_E_TOO_SHORT;
@@ -370,7 +374,7 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const TrackSet ts = track_set(c);
-    const int incr = p->m * p->tau;
+    const int incr = win_incr(p);
     SlotGeom g;
     g.max_rows = c->max_frames - incr;
     g.max_cols = c->max_frames - incr;
@@ -395,7 +399,8 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     }
     ++launches;
 
-    const bool fast = (p->crp_path == ACOSS_CRP_AUTO) && k2_fast_supported(*p, g, ts);
+    const bool fast = (p->crp_path == ACOSS_CRP_AUTO) && !p->f2_strict && !p->f3_float_acc && !p->f4_keep_last &&
+                      k2_fast_supported(*p, g, ts);
     // bytes per slot
     const size_t exact_slot = (size_t)g.max_rows * ldd * 4 + (size_t)c->max_frames * NBINS * 4 + (size_t)(g.max_rows + g.max_cols) * 4;
     const size_t common_slot = (size_t)g.crp_words * 4 + (size_t)(g.max_rows + g.max_cols) * 4 + 8 + (size_t)2 * halo_pitch * 16;
@@ -481,6 +486,11 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
             TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p,
                                (const int32_t *)c->cols.p, n, g.max_cols, ACOSS_ALIGN_DMAX, p->gamma_o, p->gamma_e,
                                scores2_dev + first, (uint32_t *)c->halo.p, halo_pitch, st, &launches));
+        if (p->f5_asymmetric) {                                  // F5: sqrt(N') / max(Q) (essentia 'asymmetric')
+            TRY(launch_score_asymmetric(scores_dev + first, (const int32_t *)c->cols.p, n, st));
+            if (scores2_dev) TRY(launch_score_asymmetric(scores2_dev + first, (const int32_t *)c->cols.p, n, st));
+            ++launches;
+        }
         t3.stop();
     }
     // fold per-pair status into one word; read back at sync time

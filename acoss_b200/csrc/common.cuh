@@ -80,6 +80,12 @@ struct KernelTimer {
     virtual void end(int id) = 0;
 };
 
+// F3 switch: the same with a float32 accumulator (std::inner_product(..., 0.f)); the accumulator variable stays a
+// double that always holds a float32 value
+__device__ __forceinline__ double acc_f32prod_f32(double acc, float a, float b) {
+    return (double)__fadd_rn((float)acc, __fmul_rn(a, b));
+}
+
 // host launchers (one per translation unit) -----------------------------------------------------
 struct Params;   // fwd
 
@@ -114,6 +120,8 @@ int launch_dp_bits(const uint32_t *bits, int64_t slot_words, int words_per_row, 
 // pair geometry (rows = n_q - m*tau, cols = n_r - m*tau) for pairs[first..first+n)
 int launch_pair_geometry(const TrackSet &ts, const int32_t *pairs, int64_t first, int n, int incr,
                          int32_t *rows, int32_t *cols, cudaStream_t st);
+// F5 switch: scores[k] = sqrtf(cols[k]) / scores[k] (essentia distanceType 'asymmetric', App. A6)
+int launch_score_asymmetric(float *scores, const int32_t *cols, int n, cudaStream_t st);
 int launch_sw_trim(uint32_t *bits, int64_t slot_words, int words_per_row, int32_t *rows, int32_t *cols, int n,
                    cudaStream_t st);
 int launch_pack_bytes(const uint8_t *mats, const int64_t *offsets, const int32_t *shapes, int n,

@@ -18,14 +18,14 @@
 __global__ void __launch_bounds__(256) exact_prep_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                          const int32_t *__restrict__ oti, int64_t first,
                                                          const int32_t *__restrict__ slot_map, int m, int tau,
-                                                         int max_frames, int max_rows, int max_cols,
+                                                         int incr, int f32acc, int max_frames, int max_rows, int max_cols,
                                                          float *__restrict__ rrot_all, float *__restrict__ aa_all,
                                                          float *__restrict__ bb_all) {
     const int slot = blockIdx.x;
     const int64_t k = slot_map ? slot_map[slot] : first + slot;
     const int q = pairs[2 * k], r = pairs[2 * k + 1], s = oti[k] % NBINS;
     const int nq = (int)(ts.offsets[q + 1] - ts.offsets[q]), nr = (int)(ts.offsets[r + 1] - ts.offsets[r]);
-    const int incr = m * tau, M = nq - incr, N = nr - incr;
+    const int M = nq - incr, N = nr - incr;
     const float *Q = ts.frames + ts.offsets[q] * NBINS;
     const float *R = ts.frames + ts.offsets[r] * NBINS;
     float *rrot = rrot_all + (int64_t)slot * max_frames * NBINS;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) exact_prep_kernel(TrackSet ts, const int3
         for (int t = 0; t < m; ++t) {
             const float *fr = src + (int64_t)t * tau * NBINS;
 #pragma unroll
-            for (int b = 0; b < NBINS; ++b) acc = acc_f32prod(acc, fr[b], fr[b]);
+            for (int b = 0; b < NBINS; ++b) acc = f32acc ? acc_f32prod_f32(acc, fr[b], fr[b]) : acc_f32prod(acc, fr[b], fr[b]);
         }
         if (isq) aa[i] = (float)acc; else bb[i - M] = (float)acc;
     }
@@ -56,8 +56,8 @@ constexpr int TR = 16, TC = 128, RPT = 2, CPT = 4, SP = 13;
 
 __global__ void __launch_bounds__(256) exact_dist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                          int64_t first, const int32_t *__restrict__ slot_map,
-                                                         int m, int tau, int max_frames, int max_rows, int max_cols,
-                                                         const float *__restrict__ rrot_all,
+                                                         int m, int tau, int incr, int f32acc, int max_frames, int max_rows,
+                                                         int max_cols, const float *__restrict__ rrot_all,
                                                          const float *__restrict__ aa_all,
                                                          const float *__restrict__ bb_all, float *__restrict__ D_all,
                                                          int64_t ldd, uint32_t *__restrict__ status) {
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) exact_dist_kernel(TrackSet ts, const int3
     const int64_t k = slot_map ? slot_map[slot] : first + slot;
     const int q = pairs[2 * k], r = pairs[2 * k + 1];
     const int nq = (int)(ts.offsets[q + 1] - ts.offsets[q]), nr = (int)(ts.offsets[r + 1] - ts.offsets[r]);
-    const int incr = m * tau, M = nq - incr, N = nr - incr;
+    const int M = nq - incr, N = nr - incr;
     const int i0 = blockIdx.y * TR, j0 = blockIdx.x * TC;
     if (i0 >= M || j0 >= N) return;
     const int span = (m - 1) * tau;
@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) exact_dist_kernel(TrackSet ts, const int3
 #pragma unroll
             for (int a = 0; a < RPT; ++a)
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) acc[a][c] = acc_f32prod(acc[a][c], qv[a], rv[c]);
+                for (int c = 0; c < CPT; ++c)
+                    acc[a][c] = f32acc ? acc_f32prod_f32(acc[a][c], qv[a], rv[c]) : acc_f32prod(acc[a][c], qv[a], rv[c]);
         }
     }
     const float *aa = aa_all + (int64_t)slot * max_rows, *bb = bb_all + (int64_t)slot * max_cols;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) exact_emit_kernel(TrackSet ts, const int3
                                                          const float *__restrict__ D_all, int64_t ldd,
                                                          const float *__restrict__ thr_q_all,
                                                          const float *__restrict__ thr_r_all, int words,
-                                                         int64_t crp_words, int64_t out_base,
+                                                         int64_t crp_words, int64_t out_base, int strict,
                                                          uint32_t *__restrict__ crp_all) {
     const int slot = blockIdx.z;
     const int64_t k = slot_map ? slot_map[slot] : first + slot;
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(256) exact_emit_kernel(TrackSet ts, const int3
     if (j < N) {
         const float d = D_all[((int64_t)slot * max_rows + i) * ldd + j];
         const float tq = thr_q_all[(k - out_base) * max_rows + i], tr = thr_r_all[(k - out_base) * max_cols + j];
-        bit = (__fsub_rn(tq, d) >= 0.f) && (__fsub_rn(tr, d) >= 0.f);
+        const float xq = __fsub_rn(tq, d), xr = __fsub_rn(tr, d);        // heaviside arguments (F2)
+        bit = strict ? (xq > 0.f && xr > 0.f) : (xq >= 0.f && xr >= 0.f);
     }
     const unsigned word = __ballot_sync(0xffffffffu, bit);
     if (lane == 0) crp_all[(k - out_base) * crp_words + (int64_t)i * words + w] = word;
@@ -239,18 +241,18 @@ int launch_k2_exact(const TrackSet &ts, const int32_t *pairs, const int32_t *oti
     // thresholds) land in chunk slot k - first, so a fallback re-run overwrites the pair's own slot.
     const int64_t out_base = first;
     if (n <= 0) return ACOSS_OK;
-    const int incr = p.m * p.tau;
+    const int incr = p.f4_keep_last ? (p.m - 1) * p.tau : p.m * p.tau;   // F4
     const float qperc = (float)((double)(p.kappa * 100.f) / 100.);   // App. A4 float32 round trip
-    exact_prep_kernel<<<n, 256, 0, st>>>(ts, pairs, oti, first, slot_map, p.m, p.tau, ts.max_frames, g.max_rows,
-                                         g.max_cols, sc.rrot, sc.aa, sc.bb);
+    exact_prep_kernel<<<n, 256, 0, st>>>(ts, pairs, oti, first, slot_map, p.m, p.tau, incr, p.f3_float_acc, ts.max_frames,
+                                         g.max_rows, g.max_cols, sc.rrot, sc.aa, sc.bb);
     CUDA_TRY(cudaGetLastError());
     const int span = (p.m - 1) * p.tau;
     const size_t smem_d = (size_t)(TR + span + TC + span) * SP * sizeof(float);
     if (smem_d > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(exact_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
     dim3 gd((g.max_cols + TC - 1) / TC, (g.max_rows + TR - 1) / TR, n);
-    exact_dist_kernel<<<gd, 256, smem_d, st>>>(ts, pairs, first, slot_map, p.m, p.tau, ts.max_frames, g.max_rows,
-                                               g.max_cols, sc.rrot, sc.aa, sc.bb, sc.D, sc.ldd, status);
+    exact_dist_kernel<<<gd, 256, smem_d, st>>>(ts, pairs, first, slot_map, p.m, p.tau, incr, p.f3_float_acc, ts.max_frames,
+                                               g.max_rows, g.max_cols, sc.rrot, sc.aa, sc.bb, sc.D, sc.ldd, status);
     CUDA_TRY(cudaGetLastError());
     const size_t smem_r = (size_t)g.max_cols * 4, smem_c = (size_t)g.max_rows * 4;
     if (smem_r > 48 * 1024)
@@ -267,7 +269,7 @@ int launch_k2_exact(const TrackSet &ts, const int32_t *pairs, const int32_t *oti
     CUDA_TRY(cudaGetLastError());
     dim3 ge((g.words + 7) / 8, g.max_rows, n);
     exact_emit_kernel<<<ge, 256, 0, st>>>(ts, pairs, first, slot_map, incr, g.max_rows, g.max_cols, sc.D, sc.ldd,
-                                          thr_q, thr_r, g.words, g.crp_words, out_base, crp);
+                                          thr_q, thr_r, g.words, g.crp_words, out_base, p.f2_strict, crp);
     CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 5;
     return ACOSS_OK;

@@ -61,7 +61,8 @@ struct PairHdr {                    // per-slot header written by fast_prep_kern
 struct FastLayout {
     size_t slot_bytes;
     size_t off_hdr, off_rrot, off_aaf, off_bbf, off_aai, off_bbi, off_lo, off_w, off_cb, off_sh, off_cnt,
-        off_cand, off_candz, off_zin, off_zout, off_rowpack, off_pool, off_pcnt, off_samp_r, off_samp_c, off_live, off_nlive;
+        off_cand, off_candz, off_zin, off_zout, off_rowpack, off_pool, off_pcnt, off_samp_r, off_samp_c, off_live, off_nlive,
+        off_lsel, off_wlist, off_wcnt, off_win;
     int max_rows, max_cols, max_frames, lines, pool_cap;
     int slog;                           // log2 of the diagonal sampling stride S
     int nst_r, nst_c;                   // sample slots per row (ceil(max_cols / S)) / per column
@@ -121,6 +122,10 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.off_samp_c = take((size_t)L.nst_c * g.max_cols * 4);      // [t = i / S][j]
     L.off_live = take((size_t)2 * SPARSE_CAP * 4);              // [side][SPARSE_CAP] lines still live after the dense level
     L.off_nlive = take(8);
+    L.off_lsel = take((size_t)L.lines * 20);                    // LineSel per line
+    L.off_wlist = take((size_t)L.lines * 4 * 8);                // WinCell list: WFLAT_PER_LINE entries per line
+    L.off_wcnt = take(4);
+    L.off_win = take((size_t)L.lines * 2 * 8 * 4);              // exact items of the window cells: [line][2][WIN_CAP]
     L.slot_bytes = align_up(o, 256);
     return L;
 }
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     for (int i = threadIdx.x; i < L.lines; i += blockDim.x) cnt[i] = 0u;
     if (threadIdx.x < 2) slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive)[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) *slot_ptr<uint32_t>(scratch, L, slot, L.off_pcnt) = 0u;
+    if (threadIdx.x == 0) { *slot_ptr<uint32_t>(scratch, L, slot, L.off_pcnt) = 0u; *slot_ptr<uint32_t>(scratch, L, slot, L.off_wcnt) = 0u; }
     __syncthreads();
     float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
     int32_t *aai = slot_ptr<int32_t>(scratch, L, slot, L.off_aai), *bbi = slot_ptr<int32_t>(scratch, L, slot, L.off_bbi);
@@ -490,52 +495,125 @@ struct Sweep {
 template <int V> struct IC { static constexpr int value = V; };
 template <bool V> struct BC { static constexpr bool value = V; };
 
-// Drives a sweep over streamed frames 0 .. nrows-1 (nrows >= 10 always: Mx >= 2).  The next frame is
-// loaded into the frame registers as soon as the dot products have consumed them, the next row's
-// parameter word right after its use: loads overlap the rest of the row, no register copies.  fn(a, param) runs for
-// rows a >= HALO, param = P[a - HALO].
+// ------------------------------------------------------------------------------------------------
+// Streamed side of a sweep: per-warp double buffer in shared memory, filled by the TMA engine
+// (cp.async.bulk global -> shared, completion on an mbarrier).  A stage holds the 9 streamed frames of one
+// round of the register ring (432 B) and the row parameters that go with them; while the warp works on a
+// stage the copy of the next one is in flight, so no warp ever waits on an L2 / HBM access for the frames
+// (with plain loads every warp of an SM stalled on the same cache line once per 2.7 rows:
+// profiles/r2_k2_tma.md).  Reads are warp-uniform LDS.128 broadcasts.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr int ST_N = 2;                            // stages per warp
+template <typename PT>
+struct alignas(16) StreamBuf {
+    static constexpr int PAL = 16 / (int)sizeof(PT);                   // parameters per 16 bytes (copy granularity)
+    static constexpr int PCOPY = (M9 + PAL - 1 + PAL - 1) / PAL * PAL; // parameters copied per stage (start aligned down)
+    ulonglong2 x[ST_N][M9][3];                     // 9 frames of 48 B
+    PT p[ST_N][PCOPY];
+    unsigned long long full[ST_N];
+};
+
+// Drives a sweep over streamed frames 0 .. nrows-1 (nrows >= 10 always: Mx >= 2) in rounds of 9 rows = one stage =
+// one round of the register ring (static ring slots, immediate shared-memory offsets).  fn(a, param) runs for rows
+// a >= HALO, param = P[a - HALO].
 template <int RC, typename PT, typename Fn>
 __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict__ X, const PT *__restrict__ P,
-                                          int nrows, Fn &&fn) {
-    const ulonglong2 *px = reinterpret_cast<const ulonglong2 *>(X);
-    ulonglong2 c0 = __ldg(px), c1 = __ldg(px + 1), c2 = __ldg(px + 2);
-    PT pc{};
-    const PT *pp = P - HALO;                       // pp[a] is the parameter of row a
-    int a = 0;
-    auto step = [&](auto uc, auto callc, auto pfc) {
-        constexpr int U = decltype(uc)::value;
-        constexpr bool CALL = decltype(callc)::value, PF = decltype(pfc)::value;
+                                          int nrows, StreamBuf<PT> *sb, int lane, Fn &&fn) {
+    using SB = StreamBuf<PT>;
+    const int nchunks = (nrows + M9 - 1) / M9;
+    auto pbase = [](int c) { return max(0, c * M9 - HALO) / SB::PAL * SB::PAL; };   // first parameter a stage holds
+    auto issue = [&](int c) {                      // one lane: start the copies of round c into stage c & 1
+        const int st = c & 1;
+        const uint32_t xb = (uint32_t)min(M9, nrows - c * M9) * (NBINS * 4), pb = SB::PCOPY * (uint32_t)sizeof(PT);
+        mbar_expect_tx(&sb->full[st], xb + pb);
+        bulk_g2s(&sb->x[st][0][0], X + (size_t)c * M9 * NBINS, xb, &sb->full[st]);
+        bulk_g2s(&sb->p[st][0], P + pbase(c), pb, &sb->full[st]);
+    };
+    if (lane == 0) {
+        mbar_init(&sb->full[0], 1);
+        mbar_init(&sb->full[1], 1);
+        mbar_fence_init();
+        issue(0);
+        if (nchunks > 1) issue(1);
+    }
+    __syncwarp();
+    int a = 0, c = 0;
+    const ulonglong2 *xs = nullptr;
+    const PT *ps = nullptr;
+    auto begin_round = [&]() {
+        const int st = c & 1;
+        mbar_wait(&sb->full[st], (uint32_t)((c >> 1) & 1));
+        xs = &sb->x[st][0][0];
+        ps = &sb->p[st][0] + (c * M9 - HALO - pbase(c));          // ps[r] = parameter of row 9c + r
+    };
+    auto end_round = [&]() {
+        __syncwarp();                              // every lane has read the stage
+        if (lane == 0 && c + ST_N < nchunks) issue(c + ST_N);
+        ++c;
+    };
+    auto step = [&](auto uc, auto callc) {
+        constexpr int U = decltype(uc)::value;     // row within the round = ring slot
+        constexpr bool CALL = decltype(callc)::value;
         int eb[RC];
-        PT pn{};
-        if (PF) pn = __ldg(pp + a + 1);            // next row's parameter: a whole row ahead of its use
-        sw.dot(c0, c1, c2, eb);
-        // the frame registers are dead now: refill them with the next row while this row finishes
-        px += 3;
-        c0 = __ldg(px); c1 = __ldg(px + 1); c2 = __ldg(px + 2);
+        const ulonglong2 x0 = xs[3 * U], x1 = xs[3 * U + 1], x2 = xs[3 * U + 2];
+        sw.dot(x0, x1, x2, eb);
         sw.template finish<U>(eb);
-        if (CALL) fn(a, pc);
-        if (PF) pc = pn;
+        if (CALL) fn(a, ps[U]);
         ++a;
     };
     // rows 0..8: the diagonal sums fill up; only row 8 produces a window
-    step(IC<0>{}, BC<false>{}, BC<false>{}); step(IC<1>{}, BC<false>{}, BC<false>{}); step(IC<2>{}, BC<false>{}, BC<false>{});
-    step(IC<3>{}, BC<false>{}, BC<false>{}); step(IC<4>{}, BC<false>{}, BC<false>{}); step(IC<5>{}, BC<false>{}, BC<false>{});
-    step(IC<6>{}, BC<false>{}, BC<false>{}); step(IC<7>{}, BC<false>{}, BC<true>{}); step(IC<8>{}, BC<true>{}, BC<true>{});
+    begin_round();
+    step(IC<0>{}, BC<false>{}); step(IC<1>{}, BC<false>{}); step(IC<2>{}, BC<false>{});
+    step(IC<3>{}, BC<false>{}); step(IC<4>{}, BC<false>{}); step(IC<5>{}, BC<false>{});
+    step(IC<6>{}, BC<false>{}); step(IC<7>{}, BC<false>{}); step(IC<8>{}, BC<true>{});
+    end_round();
 #pragma unroll 1
     while (a + M9 <= nrows) {
-        step(IC<0>{}, BC<true>{}, BC<true>{}); step(IC<1>{}, BC<true>{}, BC<true>{}); step(IC<2>{}, BC<true>{}, BC<true>{});
-        step(IC<3>{}, BC<true>{}, BC<true>{}); step(IC<4>{}, BC<true>{}, BC<true>{}); step(IC<5>{}, BC<true>{}, BC<true>{});
-        step(IC<6>{}, BC<true>{}, BC<true>{}); step(IC<7>{}, BC<true>{}, BC<true>{}); step(IC<8>{}, BC<true>{}, BC<true>{});
+        begin_round();
+        step(IC<0>{}, BC<true>{}); step(IC<1>{}, BC<true>{}); step(IC<2>{}, BC<true>{});
+        step(IC<3>{}, BC<true>{}); step(IC<4>{}, BC<true>{}); step(IC<5>{}, BC<true>{});
+        step(IC<6>{}, BC<true>{}); step(IC<7>{}, BC<true>{}); step(IC<8>{}, BC<true>{});
+        end_round();
     }
     const int rem = nrows - a;                     // 0..8 rows left, ring slots 0..rem-1
-    if (rem > 0) step(IC<0>{}, BC<true>{}, BC<true>{});
-    if (rem > 1) step(IC<1>{}, BC<true>{}, BC<true>{});
-    if (rem > 2) step(IC<2>{}, BC<true>{}, BC<true>{});
-    if (rem > 3) step(IC<3>{}, BC<true>{}, BC<true>{});
-    if (rem > 4) step(IC<4>{}, BC<true>{}, BC<true>{});
-    if (rem > 5) step(IC<5>{}, BC<true>{}, BC<true>{});
-    if (rem > 6) step(IC<6>{}, BC<true>{}, BC<true>{});
-    if (rem > 7) step(IC<7>{}, BC<true>{}, BC<true>{});
+    if (rem > 0) {
+        begin_round();
+        step(IC<0>{}, BC<true>{});
+        if (rem > 1) step(IC<1>{}, BC<true>{});
+        if (rem > 2) step(IC<2>{}, BC<true>{});
+        if (rem > 3) step(IC<3>{}, BC<true>{});
+        if (rem > 4) step(IC<4>{}, BC<true>{});
+        if (rem > 5) step(IC<5>{}, BC<true>{});
+        if (rem > 6) step(IC<6>{}, BC<true>{});
+        if (rem > 7) step(IC<7>{}, BC<true>{});
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -661,7 +739,8 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_hist_kernel(TrackSet t
     __syncwarp();
 
     const int nrows = nX - 1;                                 // streamed frames 0 .. nX-2 (F4: last frame unused)
-    run_sweep<RC, int>(sw, X, xn, nrows, [&](int, int xb) {
+    __shared__ StreamBuf<int> s_stream[WPC];
+    run_sweep<RC, int>(sw, X, xn, nrows, &s_stream[warp], lane, [&](int, int xb) {
 #pragma unroll
         for (int kk = 0; kk < RC; ++kk) {
             const int zr = xb + ynrel[kk] - sw.T[kk];
@@ -871,6 +950,7 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet t
     static_assert(RC == 4 && WPC == 4 && EMIT_CW * 32 == WPC * SW::OUTW, "a CTA must own whole CRP words");
     __shared__ uint32_t s_tile[2][EMIT_ROWS][EMIT_TW];        // [buffer][row][word]
     __shared__ uint2 s_stage[WPC][EMIT_STAGE][32];            // [warp][entry][lane]: lane-private columns, conflict-free
+    __shared__ StreamBuf<int4> s_stream[WPC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x / groups, grp = blockIdx.x - slot * groups;
     if (slot >= n) return;
@@ -977,7 +1057,7 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet t
     //   uncertain     <=> row zone or column zone or near zero
     // A near-zero cell that is certainly in is emitted as 1 and listed as well: its exact evaluation either
     // confirms a tiny distance or raises the NaN error.
-    run_sweep<RC, int4>(sw, X, rowpack, nrows, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
+    run_sweep<RC, int4>(sw, X, rowpack, nrows, &s_stream[warp], lane, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
         const int xr = rp.x - rp.y, nz = 2 * EPS - rp.y;
         const unsigned rw1 = (unsigned)(rp.z - 1);
         const int i = a - HALO;                               // CRP row
@@ -1024,28 +1104,44 @@ __global__ void __launch_bounds__(256) fast_scatter_kernel(int n, FastLayout L, 
     const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
     const int32_t *lo_c = slot_ptr<int32_t>(scratch, L, slot, L.off_lo) + L.max_rows;
     const int32_t *w_c = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + L.max_rows;
-    for (uint32_t e = e0 + threadIdx.x; e < m; e += blockDim.x) {
-        const uint2 rec = pool[e];
-        const int i = rec.x & 0x3fff, j = (rec.x >> 14) & 0x3fff;
-        const int z = (int)rec.y;
-        const int4 rp = rowpack[i];                           // {aa_fix, rowLo - 2 EPS, rowW + 4 EPS, -}
-        const int ar = z - rp.y, ac = z - (lo_c[j] - 2 * EPS);
-        const bool zz = z < 2 * EPS;                          // near-zero item: always evaluated exactly
-        const bool rz = (ar >= 0 && ar < rp.z) || zz;
-        const bool cz = ac >= 0 && ac < w_c[j] + 4 * EPS;
-        if (rz) {
-            const unsigned p = atomicAdd(&cnt[i], 1u);
-            if (p < CAND_CAP) {
-                cand[(size_t)i * CAND_CAP + p] = (uint16_t)(j | (ar < 2 * EPS ? 0x8000 : 0));
-                candz[(size_t)i * CAND_CAP + p] = z;
+    // four records per thread and round: the returning atomics of a round are independent, their latency overlaps
+    constexpr int SU = 4;
+    for (uint32_t eb = e0 + threadIdx.x; eb < m; eb += SU * blockDim.x) {
+        int ii[SU], jj[SU], zz_[SU];
+        unsigned pr[SU], pc[SU];
+        bool rz[SU], cz[SU], lowr[SU], lowc[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const uint32_t e = eb + u * blockDim.x;
+            rz[u] = cz[u] = false;
+            if (e < m) {
+                const uint2 rec = pool[e];
+                const int i = rec.x & 0x3fff, j = (rec.x >> 14) & 0x3fff;
+                const int z = (int)rec.y;
+                const int4 rp = rowpack[i];                   // {aa_fix, rowLo - 2 EPS, rowW + 4 EPS, -}
+                const int ar = z - rp.y, ac = z - (lo_c[j] - 2 * EPS);
+                const bool zz = z < 2 * EPS;                  // near-zero item: always evaluated exactly
+                rz[u] = (ar >= 0 && ar < rp.z) || zz;
+                cz[u] = ac >= 0 && ac < w_c[j] + 4 * EPS;
+                lowr[u] = ar < 2 * EPS; lowc[u] = ac < 2 * EPS;
+                ii[u] = i; jj[u] = j; zz_[u] = z;
             }
         }
-        if (cz) {
-            const int line = L.max_rows + j;
-            const unsigned p = atomicAdd(&cnt[line], 1u);
-            if (p < CAND_CAP) {
-                cand[(size_t)line * CAND_CAP + p] = (uint16_t)(i | (ac < 2 * EPS ? 0x8000 : 0));
-                candz[(size_t)line * CAND_CAP + p] = z;
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            if (rz[u]) pr[u] = atomicAdd(&cnt[ii[u]], 1u);
+            if (cz[u]) pc[u] = atomicAdd(&cnt[L.max_rows + jj[u]], 1u);
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            if (rz[u] && pr[u] < CAND_CAP) {
+                cand[(size_t)ii[u] * CAND_CAP + pr[u]] = (uint16_t)(jj[u] | (lowr[u] ? 0x8000 : 0));
+                candz[(size_t)ii[u] * CAND_CAP + pr[u]] = zz_[u];
+            }
+            if (cz[u] && pc[u] < CAND_CAP) {
+                const size_t line = (size_t)(L.max_rows + jj[u]);
+                cand[line * CAND_CAP + pc[u]] = (uint16_t)(ii[u] | (lowc[u] ? 0x8000 : 0));
+                candz[line * CAND_CAP + pc[u]] = zz_[u];
             }
         }
     }
@@ -1092,23 +1188,26 @@ __device__ __forceinline__ float exact_item(const float *__restrict__ Q, const f
 // z < zr - 2 EPS is strictly below it and every cell with z > zr + 2 EPS strictly above.  So only the window
 // cells |z - zr| <= 2 EPS (usually one or two) are evaluated in the reference's exact operation order, and the
 // exact order statistic is the (r - #cells below the window)-th smallest of them.
-constexpr int WIN_CAP = 16;         // window cells per order statistic a line can take; more -> exact path
-constexpr int WFLAT_CAP = 1024;     // window cells of the 32 lines of a CTA
+constexpr int WIN_CAP = 8;          // window cells per order statistic a line can take; more -> exact path
+constexpr int WFLAT_PER_LINE = 4;   // capacity of a pair's window-cell list, per line (average need ~2)
 
-__global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
-                                                               int64_t first, int n, FastLayout L,
-                                                               char *__restrict__ scratch, int guard, double unit,
-                                                               float *__restrict__ thr_q_all,
-                                                               float *__restrict__ thr_r_all,
-                                                               uint32_t *__restrict__ status,
-                                                               uint32_t *__restrict__ dbg) {
+struct LineSel {                    // per line, written by the rank kernel, read by the finalize kernel
+    int32_t zf, zc;                 // z order statistics of ranks floor(k), ceil(k)
+    int16_t wf, wc;                 // ranks inside the two windows
+    int16_t nf, nc;                 // window sizes
+    uint32_t bad;                   // fallback reasons found so far (0: fine); 0x80000000: nothing to select (quirk side)
+};
+static_assert(sizeof(LineSel) == 20, "FastLayout sizes LineSel as 20 bytes");
+struct WinCell {                    // one window cell to evaluate exactly
+    uint32_t cell;                  // i | j << 14
+    uint32_t dst;                   // line << 8 | slot in window 0 (0xf: none) << 4 | slot in window 1 (0xf: none)
+};
+
+// rank: 8 lanes per line, 32 lines per CTA, no CTA-wide synchronisation
+__global__ void __launch_bounds__(256) fast_rank_kernel(int n, FastLayout L, char *__restrict__ scratch) {
     __shared__ int s_z[32][CAND_CAP];
     __shared__ int s_zsel[32][2];
-    __shared__ float s_win[32][2][WIN_CAP];
     __shared__ int s_wn[32][2];
-    __shared__ uint32_t s_flat[WFLAT_CAP];                    // cell (i | j << 14) of a window member
-    __shared__ uint16_t s_fdst[WFLAT_CAP][2];                 // its slot in s_win[line][0 / 1] (0xffff: not a member)
-    __shared__ int s_nflat, s_nan;
     const int slot = blockIdx.y;
     if (slot >= n) return;
     const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
@@ -1120,7 +1219,6 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
     const bool isrow = gline < Mx;
     const int idx = isrow ? gline : gline - Mx;
     const int line = isrow ? idx : L.max_rows + idx;
-    const int64_t k = first + slot;
     const uint16_t *cand = slot_ptr<uint16_t>(scratch, L, slot, L.off_cand) + (size_t)line * CAND_CAP;
     const int32_t *candz = slot_ptr<int32_t>(scratch, L, slot, L.off_candz) + (size_t)line * CAND_CAP;
     const unsigned gmask = 0xffu << (8 * ((threadIdx.x & 31) >> 3));
@@ -1133,7 +1231,6 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
         cnt = (int)min(c, (unsigned)CAND_CAP);
     }
     if (sub == 0) { s_wn[grp][0] = 0; s_wn[grp][1] = 0; s_zsel[grp][0] = 0; s_zsel[grp][1] = 0; }
-    if (threadIdx.x == 0) { s_nflat = 0; s_nan = 0; }
     for (int p = sub; p < cnt; p += 8) {
         s_z[grp][p] = candz[p];
         nbelow += cand[p] >> 15;
@@ -1141,11 +1238,9 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
     nbelow += __shfl_xor_sync(gmask, nbelow, 1);
     nbelow += __shfl_xor_sync(gmask, nbelow, 2);
     nbelow += __shfl_xor_sync(gmask, nbelow, 4);
-    __syncthreads();
+    __syncwarp(gmask);
     const int fk = h->fk[side], ck = h->ck[side];
     const bool quirk = h->quirk[side] != 0;
-    const int32_t lo = live ? slot_ptr<int32_t>(scratch, L, slot, L.off_lo)[line] : 0;
-    const int32_t w = live ? slot_ptr<int32_t>(scratch, L, slot, L.off_w)[line] : 0;
     const int c0 = live ? slot_ptr<int32_t>(scratch, L, slot, L.off_cb)[line] - nbelow : 0;   // cells below every candidate
     const int rfk = fk - c0, rck = ck - c0;
     unsigned bad = over ? 32u : 0u;                           // reason 32: more than CAND_CAP candidates on a line
@@ -1166,9 +1261,12 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
     }
     __syncwarp(gmask);
     const int zf = s_zsel[grp][0], zc = s_zsel[grp][1];
-    // window cells go to the CTA's flat list (evaluated below by all threads: no divergence on the long exact
-    // evaluation); cells below each window are counted
+    // window cells go to the pair's flat list (evaluated by fast_exact_kernel, one thread per cell: the long
+    // exact evaluation runs on full warps); cells below each window are counted
     int nbf = 0, nbc = 0;
+    WinCell *wl = slot_ptr<WinCell>(scratch, L, slot, L.off_wlist);
+    uint32_t *wcnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_wcnt);
+    const uint32_t wcap = (uint32_t)WFLAT_PER_LINE * (uint32_t)L.lines;
     if (sel && !bad) {
         for (int p = sub; p < cnt; p += 8) {
             const int v = s_z[grp][p];
@@ -1178,65 +1276,103 @@ __global__ void __launch_bounds__(256) fast_resolve_thr_kernel(TrackSet ts, cons
             if (inf || inc) {
                 const int other = cand[p] & 0x7fff;
                 const int i = isrow ? idx : other, j = isrow ? other : idx;
-                const int sf = inf ? atomicAdd(&s_wn[grp][0], 1) : WIN_CAP, sc = inc ? atomicAdd(&s_wn[grp][1], 1) : WIN_CAP;
-                const int e = atomicAdd(&s_nflat, 1);
-                if (e < WFLAT_CAP) {
-                    s_flat[e] = (uint32_t)i | ((uint32_t)j << 14);
-                    s_fdst[e][0] = (uint16_t)(sf < WIN_CAP ? grp * WIN_CAP + sf : 0xffff);
-                    s_fdst[e][1] = (uint16_t)(sc < WIN_CAP ? grp * WIN_CAP + sc : 0xffff);
+                const int sf = inf ? atomicAdd(&s_wn[grp][0], 1) : 0xf, sc = inc ? atomicAdd(&s_wn[grp][1], 1) : 0xf;
+                const uint32_t e = atomicAdd(wcnt, 1u);
+                if (e < wcap) {
+                    WinCell wc;
+                    wc.cell = (uint32_t)i | ((uint32_t)j << 14);
+                    wc.dst = ((uint32_t)line << 8) | ((uint32_t)min(sf, 0xf) << 4) | (uint32_t)min(sc, 0xf);
+                    wl[e] = wc;
                 }
             }
         }
     }
     nbf += __shfl_xor_sync(gmask, nbf, 1); nbf += __shfl_xor_sync(gmask, nbf, 2); nbf += __shfl_xor_sync(gmask, nbf, 4);
     nbc += __shfl_xor_sync(gmask, nbc, 1); nbc += __shfl_xor_sync(gmask, nbc, 2); nbc += __shfl_xor_sync(gmask, nbc, 4);
-    __syncthreads();
-    {
-        const int nflat = min(s_nflat, WFLAT_CAP);
-        const int q = pairs[2 * k];
-        const float *Q = ts.frames + ts.offsets[q] * NBINS;
-        const float *R = slot_ptr<float>(scratch, L, slot, L.off_rrot);
-        const float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
-        for (int e = threadIdx.x; e < nflat; e += blockDim.x) {
-            const uint32_t cell = s_flat[e];
-            const int i = cell & 0x3fff, j = cell >> 14;
-            const float item = exact_item(Q, R, i, j, aaf[i], bbf[j]);
-            if (item != item || item < 0.f) s_nan = 1;        // sqrtf of a negative item is the reference's NaN (F7)
-            const unsigned d0 = s_fdst[e][0], d1 = s_fdst[e][1];
-            if (d0 != 0xffffu) s_win[d0 / WIN_CAP][0][d0 % WIN_CAP] = item;
-            if (d1 != 0xffffu) s_win[d1 / WIN_CAP][1][d1 % WIN_CAP] = item;
-        }
-        if (threadIdx.x == 0 && nflat) atomicAdd(&dbg[25], (unsigned)nflat);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_nan) atomicOr(&status[k], PAIR_ST_NAN);
-        if (s_nflat > WFLAT_CAP) atomicOr(&status[k], PAIR_ST_FALLBACK | 128u);
-    }
+    __syncwarp(gmask);
     if (!live || sub != 0) return;
+    LineSel ls;
+    ls.zf = zf; ls.zc = zc;
+    ls.nf = (int16_t)min(s_wn[grp][0], 0x7fff); ls.nc = (int16_t)min(s_wn[grp][1], 0x7fff);
+    ls.wf = (int16_t)max(min(rfk - nbf, 0x7fff), -1); ls.wc = (int16_t)max(min(rck - nbc, 0x7fff), -1);
+    ls.bad = sel ? bad : 0x80000000u;
+    slot_ptr<LineSel>(scratch, L, slot, L.off_lsel)[line] = ls;
+}
+
+// exact evaluation of the window cells: one thread per cell of the pair's flat list
+__global__ void __launch_bounds__(256) fast_exact_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n,
+                                                         FastLayout L, char *__restrict__ scratch,
+                                                         uint32_t *__restrict__ status, uint32_t *__restrict__ dbg) {
+    const int slot = blockIdx.y;
+    if (slot >= n) return;
+    const uint32_t wcap = (uint32_t)WFLAT_PER_LINE * (uint32_t)L.lines;
+    const uint32_t cntv = *slot_ptr<uint32_t>(scratch, L, slot, L.off_wcnt);
+    const uint32_t m = min(cntv, wcap);
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k = first + slot;
+    if (e == 0) {
+        if (cntv > wcap) atomicOr(&status[k], PAIR_ST_FALLBACK | 128u);   // reason 128: window-cell list overflow
+        if (m) atomicAdd(&dbg[25], m);
+    }
+    if (e >= m) return;
+    const WinCell wc = slot_ptr<WinCell>(scratch, L, slot, L.off_wlist)[e];
+    const int i = wc.cell & 0x3fff, j = wc.cell >> 14;
+    const int q = pairs[2 * k];
+    const float *Q = ts.frames + ts.offsets[q] * NBINS;
+    const float *R = slot_ptr<float>(scratch, L, slot, L.off_rrot);
+    const float item = exact_item(Q, R, i, j, slot_ptr<float>(scratch, L, slot, L.off_aaf)[i],
+                                  slot_ptr<float>(scratch, L, slot, L.off_bbf)[j]);
+    if (item != item || item < 0.f) atomicOr(&status[k], PAIR_ST_NAN);   // sqrtf of a negative item is the reference's NaN (F7)
+    const uint32_t line = wc.dst >> 8, sf = (wc.dst >> 4) & 0xf, sc = wc.dst & 0xf;
+    float *win = slot_ptr<float>(scratch, L, slot, L.off_win) + (size_t)line * 2 * WIN_CAP;
+    if (sf < WIN_CAP) win[sf] = item;
+    if (sc < WIN_CAP) win[WIN_CAP + sc] = item;
+}
+
+// finalize: one thread per line picks the exact order statistics inside the two windows and forms the threshold
+__global__ void __launch_bounds__(128) fast_thr_kernel(int64_t first, int n, FastLayout L, char *__restrict__ scratch, int guard,
+                                                       double unit, float *__restrict__ thr_q_all,
+                                                       float *__restrict__ thr_r_all, uint32_t *__restrict__ status) {
+    const int slot = blockIdx.y;
+    if (slot >= n) return;
+    const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
+    const int Mx = h->Mx, Nx = h->Nx;
+    const int gline = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gline >= Mx + Nx) return;
+    const bool isrow = gline < Mx;
+    const int idx = isrow ? gline : gline - Mx;
+    const int line = isrow ? idx : L.max_rows + idx;
+    const int side = isrow ? 0 : 1;
+    const int64_t k = first + slot;
+    const LineSel ls = slot_ptr<LineSel>(scratch, L, slot, L.off_lsel)[line];
+    const int32_t lo = slot_ptr<int32_t>(scratch, L, slot, L.off_lo)[line];
+    const int32_t w = slot_ptr<int32_t>(scratch, L, slot, L.off_w)[line];
+    unsigned bad = ls.bad & 0x7fffffffu;
     float thr = 0.f;
-    int zin = -0x40000000, zout = -0x40000000;                // thr = 0 (F1 quirk): only an exact zero distance is in, and near-zero cells are always evaluated exactly
-    if (sel && !bad) {
-        const int nf = s_wn[grp][0], nc = s_wn[grp][1];
-        const int wf = rfk - nbf, wc = rck - nbc;             // ranks inside the windows
+    int zin = -0x40000000, zout = -0x40000000;   // thr = 0 (F1 quirk): only an exact zero distance is in, and near-zero cells are always evaluated exactly
+    if (!(ls.bad & 0x80000000u) && !bad) {
+        const int nf = ls.nf, nc = ls.nc, wf = ls.wf, wc = ls.wc;
         if (nf > WIN_CAP || nc > WIN_CAP) bad |= 128u;        // reason 128: too many cells within 2 EPS of an order statistic
         else if (wf < 0 || wf >= nf || wc < 0 || wc >= nc) bad |= 256u;   // reason 256: window rank inconsistent
         else {
+            const float *win = slot_ptr<float>(scratch, L, slot, L.off_win) + (size_t)line * 2 * WIN_CAP;
+            float vf[WIN_CAP], vc[WIN_CAP];
+#pragma unroll
+            for (int a = 0; a < WIN_CAP; ++a) { vf[a] = (a < nf) ? win[a] : 0.f; vc[a] = (a < nc) ? win[WIN_CAP + a] : 0.f; }
             float ifk = 0.f, ick = 0.f;
-            for (int a = 0; a < nf; ++a) {
-                const float v = s_win[grp][0][a];
-                int rank = 0;
-                for (int b = 0; b < nf; ++b) { const float v2 = s_win[grp][0][b]; rank += (v2 < v) || (v2 == v && b < a); }
-                if (rank == wf) ifk = v;
-            }
-            for (int a = 0; a < nc; ++a) {
-                const float v = s_win[grp][1][a];
-                int rank = 0;
-                for (int b = 0; b < nc; ++b) { const float v2 = s_win[grp][1][b]; rank += (v2 < v) || (v2 == v && b < a); }
-                if (rank == wc) ick = v;
+#pragma unroll
+            for (int a = 0; a < WIN_CAP; ++a) {
+                int rf = 0, rc = 0;
+#pragma unroll
+                for (int b = 0; b < WIN_CAP; ++b) {
+                    rf += (b < nf) && ((vf[b] < vf[a]) || (vf[b] == vf[a] && b < a));
+                    rc += (b < nc) && ((vc[b] < vc[a]) || (vc[b] == vc[a] && b < a));
+                }
+                if (a < nf && rf == wf) ifk = vf[a];
+                if (a < nc && rc == wc) ick = vc[a];
             }
             // the a-priori bound |z - item / unit| <= EPS, checked on the selected cells (with margin)
-            if (fabs((double)ifk / unit - (double)zf) > (double)(2 * EPS) || fabs((double)ick / unit - (double)zc) > (double)(2 * EPS))
+            if (fabs((double)ifk / unit - (double)ls.zf) > (double)(2 * EPS) || fabs((double)ick / unit - (double)ls.zc) > (double)(2 * EPS))
                 bad |= 512u;                                  // reason 512: fixed-point bound violated
             const float sfk = __fsqrt_rn(ifk), sck = __fsqrt_rn(ick);
             const float kf = h->kf[side];
@@ -1431,8 +1567,9 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     CUDA_TRY(cudaGetLastError());
     te(K2K_SCATTER);
     tb(K2K_THR);
-    fast_resolve_thr_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(ts, pairs, first, n, L, base, p.integer_guard, unit,
-                                                                       thr_q, thr_r, status, dbg);
+    fast_rank_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(n, L, base);
+    fast_exact_kernel<<<dim3((WFLAT_PER_LINE * lines + 255) / 256, n), 256, 0, st>>>(ts, pairs, first, n, L, base, status, dbg);
+    fast_thr_kernel<<<dim3((lines + 127) / 128, n), 128, 0, st>>>(first, n, L, base, p.integer_guard, unit, thr_q, thr_r, status);
     CUDA_TRY(cudaGetLastError());
     te(K2K_THR);
     tb(K2K_BITS);
@@ -1440,7 +1577,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
                                                                                       g.words, g.crp_words, status, dbg);
     CUDA_TRY(cudaGetLastError());
     te(K2K_BITS);
-    if (launches) *launches += 15;
+    if (launches) *launches += 17;
     return ACOSS_OK;
 }
 

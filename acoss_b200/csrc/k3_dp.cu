@@ -572,6 +572,17 @@ __global__ void __launch_bounds__(128) sw_trim_kernel(uint32_t *__restrict__ bit
     if (threadIdx.x == 0) { rows[k] = R > 0 ? R - 1 : 0; cols[k] = C > 0 ? C - 1 : 0; }
 }
 
+__global__ void score_asymmetric_kernel(float *__restrict__ scores, const int32_t *__restrict__ cols, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) scores[k] = __fdiv_rn(__fsqrt_rn((float)cols[k]), scores[k]);
+}
+int launch_score_asymmetric(float *scores, const int32_t *cols, int n, cudaStream_t st) {
+    if (n <= 0) return ACOSS_OK;
+    score_asymmetric_kernel<<<(n + 255) / 256, 256, 0, st>>>(scores, cols, n);
+    CUDA_TRY(cudaGetLastError());
+    return ACOSS_OK;
+}
+
 int launch_sw_trim(uint32_t *bits, int64_t slot_words, int words_per_row, int32_t *rows, int32_t *cols, int n,
                    cudaStream_t st) {
     if (n <= 0) return ACOSS_OK;

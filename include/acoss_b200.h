@@ -62,6 +62,13 @@ typedef struct acoss_params {
                             /* ACOSS_ALIGN_SW: smith_waterman_constrained over the same CRP        */
     int32_t integer_guard;  /* F1 switch: 0 = essentia behaviour (integer rank -> threshold 0)     */
     int32_t crp_path;       /* ACOSS_CRP_AUTO / ACOSS_CRP_EXACT                                    */
+    /* Switches for the points where the restatement of essentia is uncertain (SURVEY.md App. A F2-F5;    */
+    /* the oracle carries the same switches).  All 0 = the App. A defaults.  Pairs scored with F2-F4 set   */
+    /* take the exact CRP path (the fast path's bounds are derived for the defaults).                      */
+    int32_t f2_strict;      /* F2: 1 = heaviside(x) = 1 iff x > 0 (d == threshold is NOT similar)          */
+    int32_t f3_float_acc;   /* F3: 1 = dotProduct accumulates in float32 (init 0.f) instead of float64      */
+    int32_t f4_keep_last;   /* F4: 1 = n - (m-1)*tau stacked frames (the natural count) instead of n - m*tau */
+    int32_t f5_asymmetric;  /* F5: 1 = distanceType 'asymmetric': score = sqrt(N') / max(Q)                  */
 } acoss_params;
 
 /* Fills *p with the reference defaults (m=9, tau=1, kappa=0.095, oti=1, noti=12, 0.5, 0.5, Qmax). */

@@ -178,18 +178,23 @@ def thresholds(d: np.ndarray, kappa, *, integer_guard: bool = False):
 
 
 # --------------------------------------------------------------------------- A5
-def binarize(d: np.ndarray, thr_q: np.ndarray, thr_r: np.ndarray) -> np.ndarray:
-    """csm = heaviside(thrQ[i]-d) * heaviside(thrR[j]-d), heaviside(x)=1 iff x>=0 (F2).
+def binarize(d: np.ndarray, thr_q: np.ndarray, thr_r: np.ndarray, *, strict: bool = False) -> np.ndarray:
+    """csm = heaviside(thrQ[i]-d) * heaviside(thrR[j]-d), heaviside(x)=1 iff x>=0 (F2; ``strict=True`` is the
+    alternative x>0, i.e. d == thr does not count as similar).
     Shape (M', N') = (query, reference) (F8).  uint8 {0,1}; NaN distances raise (F7)."""
     if np.isnan(d).any():
         raise Serra09Error("NaN distance (negative squared distance, F7): non-binary CRP")
-    sx = (thr_q[:, None] - d) >= 0
-    sy = (thr_r[None, :] - d) >= 0
+    if strict:
+        sx = (thr_q[:, None] - d) > 0
+        sy = (thr_r[None, :] - d) > 0
+    else:
+        sx = (thr_q[:, None] - d) >= 0
+        sy = (thr_r[None, :] - d) >= 0
     return (sx & sy).astype(np.uint8)
 
 
 def chroma_cross_similarity(query, reference, *, m=9, tau=1, kappa=0.095, oti=True, noti=12,
-                            f64_accumulate=True, integer_guard=False, drop_one=True,
+                            f64_accumulate=True, integer_guard=False, drop_one=True, strict=False,
                             return_debug=False):
     """essentia ChromaCrossSimilarity (otiBinary=False, streaming=False). App. A1-A5."""
     query = np.ascontiguousarray(query, dtype=F32)
@@ -208,16 +213,18 @@ def chroma_cross_similarity(query, reference, *, m=9, tau=1, kappa=0.095, oti=Tr
         raise Serra09Error("fewer than 2 stacked frames: essentia percentile() is undefined (F9)")
     d = pairwise_distance(qs, rs, f64_accumulate=f64_accumulate)
     thr_q, thr_r = thresholds(d, kappa, integer_guard=integer_guard)
-    crp = binarize(d, thr_q, thr_r)
+    crp = binarize(d, thr_q, thr_r, strict=strict)
     if return_debug:
         return crp, dict(oti=s, d=d, thr_q=thr_q, thr_r=thr_r)
     return crp
 
 
 # --------------------------------------------------------------------------- A6
-def qmax(crp: np.ndarray, gamma_o: float = 0.5, gamma_e: float = 0.5, *, return_matrix=False):
+def qmax(crp: np.ndarray, gamma_o: float = 0.5, gamma_e: float = 0.5, *, return_matrix=False,
+         asymmetric: bool = False):
     """essentia CoverSongSimilarity alignmentType='serra09', distanceType='symmetric'
-    (F5: returns max(Q), un-normalised).  Row-vectorised float32 restatement of
+    (F5: returns max(Q), un-normalised; ``asymmetric=True`` is the other distanceType as App. A6 records it,
+    float32 sqrt(N') / max(Q) with N' the reference axis).  Row-vectorised float32 restatement of
 
         Q[i][j] = max3(Q[i-1][j-1], Q[i-2][j-1], Q[i-1][j-2]) + 1              if crp[i][j]==1
                 = max(0, Q[p] - gamma(crp[p]) for the same three p)            otherwise
@@ -239,6 +246,9 @@ def qmax(crp: np.ndarray, gamma_o: float = 0.5, gamma_e: float = 0.5, *, return_
         miss = np.maximum(np.maximum(p1 - g1, p2 - g2), np.maximum(p3 - g3, F32(0))).astype(F32)
         Q[i, 2:] = np.where(c[i, 2:], hit, miss)
     score = F32(Q.max()) if Q.size else F32(0)
+    if asymmetric:
+        with np.errstate(divide="ignore"):
+            score = F32(np.sqrt(F32(N)) / score)
     if return_matrix:
         return score, Q
     return score
@@ -313,5 +323,6 @@ def serra09_pair(query, reference, *, m=9, tau=1, kappa=0.095, oti=True, gamma_o
                  **flags) -> np.float32:
     """One ``Serra09.similarity`` pair: the value written to ``Ds['main'][i][j]``
     (``rqa_serra09.py:66-69``)."""
+    asym = bool(flags.pop("asymmetric", False))
     crp = chroma_cross_similarity(query, reference, m=m, tau=tau, kappa=kappa, oti=oti, **flags)
-    return qmax(crp, gamma_o, gamma_e)
+    return qmax(crp, gamma_o, gamma_e, asymmetric=asym)

@@ -30,7 +30,8 @@ def test_params_struct_matches_defaults():
     p = _lib.default_params()
     assert (p.m, p.tau, p.oti, p.noti, p.align, p.integer_guard, p.crp_path) == (9, 1, 1, 12, 0, 0, 0)
     assert abs(p.kappa - 0.095) < 1e-7 and p.gamma_o == 0.5 and p.gamma_e == 0.5
-    assert C.sizeof(_lib.Params) == 40
+    assert (p.f2_strict, p.f3_float_acc, p.f4_keep_last, p.f5_asymmetric) == (0, 0, 0, 0)
+    assert C.sizeof(_lib.Params) == 56
     assert _lib.load().acoss_compiled_sm() == 100
 
 
