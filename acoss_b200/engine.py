@@ -144,7 +144,7 @@ class Engine:
     def dump_pair(self, q: int, r: int, params: Params | None = None):
         """-> dict(oti, crp uint8 (M', N'), thr_q, thr_r, score) for one pair (debug API)."""
         params = params or default_params()
-        incr = params.m * params.tau
+        incr = (params.m - 1) * params.tau if params.f4_keep_last else params.m * params.tau   # F4
         M = int(self.offsets[q + 1] - self.offsets[q]) - incr
         N = int(self.offsets[r + 1] - self.offsets[r]) - incr
         if M < 2 or N < 2:

@@ -26,6 +26,7 @@ Output: ONE JSON line on rank 0 (contract in the task statement), with
 DESIGN.md §5) on the same config/metric/unit.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -38,10 +39,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (dram__bytes_read.sum +
-# dram__bytes_write.sum of one fast_emit_kernel launch, divided by the pairs of that launch)
-EMIT_DRAM_BYTES_PER_PAIR = 1.836e6
-EMIT_TRAFFIC_SOURCE = "profiles/r1_k2_s10.md (2048-pair launch: 1.62 GB read + 2.14 GB written)"
+# Per-pair constants of the dominant kernel (fast_emit_kernel) measured by the committed `ncu --set full` capture of
+# THIS build: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) and executed warp instructions
+# (smsp__inst_executed.sum) of one launch divided by its pairs.  profiles/make_constants.py writes the file from the
+# .ncu-rep kept beside it; it records the git hash it was taken at.
+CONSTANTS_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "k2_constants.json")
+
+
+def load_constants():
+    try:
+        with open(CONSTANTS_FILE) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 METRIC = "all-pairs alignments/sec"
 UNIT = "pairs/s"
@@ -171,6 +181,41 @@ def earlyfusion_leg(eng, sm_mhz):
                              "parity_on_sample": bool(same)}}
 
 
+def c4s_leg(device):
+    """Informational: the pair pipeline on C4s-shaped tracks (the Da-TACOS clique layout at ~500 frames per track, what
+    the x40 median downsampling of a 4-minute song gives: SURVEY 8d), 1 000 tracks, 131 072 random pairs per call, host
+    pair list in / host scores out, with a parity sample against the C oracle."""
+    from acoss_b200 import Engine, pack_tracks, synthetic
+    from oracle import serra09_c as oc
+    tracks, labels = synthetic.config_dataset("C4s", max_tracks=1000)
+    frames, offs = pack_tracks(tracks)
+    pairs = synthetic.all_pairs_upper(len(tracks))
+    pairs = pairs[np.random.default_rng(3).permutation(len(pairs))[:131072]].astype(np.int32)
+    lens = np.diff(offs)
+    cells = int(((lens[pairs[:, 0]] - 9) * (lens[pairs[:, 1]] - 9)).sum())
+    with Engine(device) as e2:
+        e2.set_tracks(frames, offs)
+        e2.score_pairs(pairs[:4096])
+        e2.score_pairs(pairs)
+        e2.set_profiling(True)
+        reps, times = 3, []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            got = e2.score_pairs(pairs)
+            times.append(time.perf_counter() - t0)
+        st = e2.last_stats()
+        stage = {k: v / reps for k, v in e2.stage_ms().items()}
+        kms = {k: v / reps for k, v in e2.kernel_ms().items()}
+    sel = np.random.default_rng(4).permutation(len(pairs))[:256]
+    want = oc.pairs(frames, offs, pairs[sel], oc.params(hoist_norms=True), nthreads=os.cpu_count() or 1)
+    dt = min(times)
+    return {"workload": "C4s: Da-TACOS-shaped cliques at ~500 frames per track, 1000 tracks, %d pairs per call" % len(pairs),
+            "e2e": {"value": len(pairs) / dt, "unit": UNIT, "h2d_bytes_per_step": int(pairs.nbytes), "d2h_bytes_per_step": int(got.nbytes),
+                    "api": "Engine.score_pairs (acoss_score_pairs), host buffers"},
+            "gcups": cells / dt / 1e9, "stage_ms_per_call": stage, "k2_kernel_ms_per_call": kms,
+            "fallback_pairs": st["fallback_pairs"], "parity_on_sample": bool(np.array_equal(got[sel], want))}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU port of the reference path, all host threads, bounded steps."""
     if rank != 0:
@@ -291,7 +336,9 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     stage = eng.stage_ms()
+    kernel_ms_timed = eng.kernel_ms()
     k2_debug = eng.debug_counters()                            # of the last timed step
+    fallback_timed = eng.last_stats()["fallback_pairs"]
     eng.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local)
     if world > 1:
@@ -302,57 +349,102 @@ def main():
     value = world * args.steps * P / (ms_max / 1e3)
     gcups = world * cells / (ms_max / 1e3) / 1e9
 
-    # ---- end to end through the plugin API (host buffers in, host score matrix out) -----------
+    # ---- gather parity (N > 1): every rank re-scores a sample of ANOTHER rank's shard ----------------------
+    gather_parity = None
+    if world > 1:
+        other = (rank + 1) % world
+        theirs = pairs[perm[other * need:(other + 1) * need]]
+        sel = args.warmup * P + np.random.default_rng(100 + rank).permutation(args.steps * P)[:64]
+        mine_of_theirs = eng.score_pairs(theirs[sel].astype(np.int32), params)
+        got = gathered[other * need:(other + 1) * need].cpu().numpy()[sel]
+        ok = torch.tensor([1 if np.array_equal(mine_of_theirs, got) else 0], dtype=torch.int32, device="cuda:%d" % local)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_parity = bool(int(ok.item()))
+
+    # ---- end to end: the product path, all_pairwise_distributed over the WHOLE C3 pair list (strong scaling) -----
+    # host pair tiles in, host score tiles out (acoss_score_pairs), NCCL gather of the score slices, assembly of the
+    # N x N matrix and its symmetrisation; then the reference's tail on rank 0 (normalize_by_length, getEvalStatistics)
+    from acoss_b200.distributed import all_pairwise_distributed
     feats = [dict(hpcp=t_, label=str(l)) for t_, l in zip(tracks, labels)]
     cache = os.path.join("/tmp", "acoss_bench_cache_%d" % rank)
-    import contextlib
     with contextlib.redirect_stdout(sys.stderr):               # keep stdout to the one JSON line
         alg = Serra09(None, None, features=feats, downsample_fac=1, shortname="bench%d" % rank, device=local,
-                      cachedir=cache, engine=eng)
+                      cachedir=cache, engine=eng, tile_pairs=P)
     alg._resident = True                                       # tracks already resident in this engine
     alg.crp_path = params.crp_path
-    host_pairs = [mine[k * P:(k + 1) * P].astype(np.int64) for k in range(total_steps)]
-    for k in range(min(args.warmup, 2)):
-        alg.similarity(host_pairs[k])
+    alg.similarity(pairs[:4096].astype(np.int64))              # warm-up of the host path (pinned staging, allocations)
+    alg.Ds["main"][:, :] = 0
     barrier()
     te0 = time.perf_counter()
-    for k in range(args.warmup, total_steps):
-        alg.similarity(host_pairs[k])
+    all_pairwise_distributed(alg, symmetric=True)
     torch.cuda.synchronize()
     te = time.perf_counter() - te0
     t = torch.tensor([te], dtype=torch.float64, device="cuda:%d" % local)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * args.steps * P / float(t.item())
+    e2e_s = float(t.item())
+    e2e_val = len(pairs) / e2e_s
+    tail = None
+    if rank == 0:
+        with contextlib.redirect_stdout(sys.stderr):
+            tt0 = time.perf_counter()
+            alg.normalize_by_length()
+            tt1 = time.perf_counter()
+            MR, MRR, MDR, MAP, tops = alg.getEvalStatistics("main")
+            tt2 = time.perf_counter()
+        tail = {"normalize_by_length_s": tt1 - tt0, "getEvalStatistics_s": tt2 - tt1, "MAP": float(MAP), "MR1": float(MR)}
+        try:
+            os.remove("results_bench0_Serra09.csv")
+        except OSError:
+            pass
     alg.cleanup_memmap()
 
-    # ---- roofline of the dominant stage (K2 = CRP construction) -------------------------------
+    # ---- roofline of the dominant kernel (fast_emit_kernel, the sweep that writes the bit-packed CRP) -------------
     k2_ms = stage["k2_crp"]
     k3_ms = stage["k3_dp"]
     emit_ms = stage.get("k2_emit", 0.0)
     emit_launches = max(1, eng.last_stats().get("chunks", 1)) * args.steps
-    # dominant kernel: fast_emit_kernel (the sweep that writes the bit-packed CRP).  Algorithmic bytes of one
-    # launch: 48 (n_q + n_r) frame bytes in + M'N'/8 CRP bytes out, summed over its pairs.
+    # Algorithmic bytes of one launch: 48 (n_q + n_r) frame bytes in + M'N'/8 CRP bytes out per pair.
     ach_gbs = bytes_k2 / (emit_ms / 1e3) / 1e9 if emit_ms > 0 else None
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
-    issue_peak = 148 * 128 * sm_mhz * 1e6                      # lane-instructions / s at the measured clock
+    issue_peak = 148 * 128 * sm_mhz * 1e6                      # lane-instructions / s: 4 schedulers x 32 lanes x 148 SMs
+    fp32_peak = 2 * issue_peak                                 # flop / s: one FMA per lane and clock
     pairs_per_launch = args.steps * P / emit_launches
+    consts = load_constants() or {}
+    ce = consts.get("emit", {})
+    emit_s = emit_ms / 1e3
+    traffic = int(ce["dram_bytes_per_pair"] * pairs_per_launch) if "dram_bytes_per_pair" in ce else None
+    lane_inst = ce.get("lane_inst_per_cell")
+    binding = None
+    if emit_s > 0:
+        binding = {"kind": "instruction issue (the roofline that binds: K = 12 contractions + integer classification, "
+                           "no float CSM in HBM)",
+                   "achieved_lane_inst_per_s": (lane_inst * cells / emit_s) if lane_inst else None,
+                   "peak_lane_inst_per_s": issue_peak,
+                   "frac": (lane_inst * cells / emit_s / issue_peak) if lane_inst else None,
+                   "lane_inst_per_cell": lane_inst,
+                   "fp32": {"flop_per_cell": 30, "achieved_tflops": 30 * cells / emit_s / 1e12,
+                            "peak_tflops": fp32_peak / 1e12, "frac": 30 * cells / emit_s / fp32_peak,
+                            "peak_kind": "nominal: 148 SMs x 128 lanes x 2 flop at the sampled SM clock (no measured FP32 peak)"},
+                   "constants_from": consts.get("source"), "constants_git": consts.get("git")}
     roofline = {"bound": "hbm", "kernel": "fast_emit_kernel<4> (K2 emit sweep)", "achieved": ach_gbs, "peak": hbm_peak,
                 "unit": "GB/s", "frac": (ach_gbs / hbm_peak) if ach_gbs else None,
-                "traffic": int(EMIT_DRAM_BYTES_PER_PAIR * pairs_per_launch),
-                "traffic_source": EMIT_TRAFFIC_SOURCE,
+                "traffic": traffic,
+                "traffic_source": consts.get("source"),
                 "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, sustained copy)" if peak_kind == "measured" else peak_kind,
                 "algorithmic_bytes_per_launch": int(bytes_k2 / emit_launches),
                 "launches": emit_launches, "ms_per_launch": emit_ms / emit_launches,
                 "k2_stage_ms_per_step": k2_ms / args.steps, "emit_share_of_step": emit_ms / ms,
-                "note": "ALU-issue bound by design (no float CSM in HBM): the HBM fraction is expected to be small; "
-                        "roofline_alu gives cell updates against the lane-instruction issue peak"}
+                "binding": binding,
+                "note": "the kernel is instruction-issue bound by design (no float CSM in HBM), so the HBM fraction is small; "
+                        "`binding` is the roofline that binds"}
     roofline_alu = {"k2_cells_per_s": cells / (k2_ms / 1e3) if k2_ms > 0 else None,
                     "k3_cells_per_s": cells / (k3_ms / 1e3) if k3_ms > 0 else None,
                     "issue_peak_lane_ops_per_s": issue_peak,
                     "k2_lane_ops_per_cell_at_peak": issue_peak / (cells / (k2_ms / 1e3)) if k2_ms > 0 else None,
                     "k3_frac_of_5op_int_roofline": (5 * cells / (k3_ms / 1e3)) / issue_peak if k3_ms > 0 else None,
                     "emit_cells_per_s": cells / (emit_ms / 1e3) if emit_ms > 0 else None,
+                    "k2_kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms_timed.items()},
                     "stage_share": {"k1": stage["k1_oti"] / ms, "k2": k2_ms / ms, "k3": k3_ms / ms,
                                     "k2_emit": emit_ms / ms}}
 
@@ -368,10 +460,27 @@ def main():
         tc = time.perf_counter() - tc0
         # parity spot check on the sample: GPU scores must equal the oracle's
         got = eng.score_pairs(idx.astype(np.int32), params)
+        # the same port with the norms hoisted out of the cell loop (essentia re-evaluates a.a and b.b for every cell;
+        # hoisting them is the first thing a CPU optimiser would do): reported beside the essentia-shaped number
+        n_h = max(cores, 8) * 4
+        th0 = time.perf_counter()
+        hs = oc.pairs(frames, offs, idx[:n_h], oc.params(hoist_norms=True), nthreads=cores)
+        th = time.perf_counter() - th0
         cpu = {"value": n_s / tc, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d random pairs of the timed C3 batches, %.1f s of CPU" % (n_s, tc),
                "gcups": algorithmic_bytes(lens, idx)[0] / tc / 1e9,
-               "parity_on_sample": bool(np.array_equal(got, ref_scores))}
+               "parity_on_sample": bool(np.array_equal(got, ref_scores)),
+               "hoisted": {"value": n_h / th, "unit": UNIT, "gcups": algorithmic_bytes(lens, idx[:n_h])[0] / th / 1e9,
+                           "sample": "%d of the same pairs, norms hoisted, %.1f s" % (n_h, th),
+                           "same_scores": bool(np.array_equal(hs, ref_scores[:n_h]))}}
+
+    # ---- secondary workload: the realistic track length (C4s: ~500 frames = a 4-minute song after the x40 median) ----
+    c4s_line = None
+    if rank == 0 and world == 1:
+        try:
+            c4s_line = c4s_leg(local)
+        except Exception as e:
+            c4s_line = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- secondary workload (not the headline): EarlyFusion pair scoring, BASELINE.json configs[1] shape ----
     ef_line = None
@@ -391,14 +500,21 @@ def main():
                            "l2": "inputs larger than L2: each step streams >= %.1f GB of CRP scratch" % (bytes_k2 / args.steps / 1e9),
                            "track_upload_s": setup_s},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(P * 8), "d2h_bytes_per_step": int(P * 4),
-                        "api": "acoss_b200.serra09.Serra09.similarity(idxs) -> host score matrix"},
+                        "api": "acoss_b200.distributed.all_pairwise_distributed(Serra09) over the whole C3 pair list: host pair "
+                               "tiles of %d in / host score tiles out (acoss_score_pairs), score slices gathered (NCCL at N > 1), "
+                               "N x N matrix assembled and symmetrised into Ds" % P,
+                        "scaling": "strong", "pairs": int(len(pairs)), "seconds": e2e_s,
+                        "rank0_tail": tail},
+                "gather_parity": gather_parity,
                 "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "roofline_alu": roofline_alu, "cpu_baseline": cpu,
-                "fallback_pairs": eng.last_stats()["fallback_pairs"], "k2_debug": k2_debug,
-                "earlyfusion": ef_line}
+                "fallback_pairs": fallback_timed, "k2_debug": k2_debug,
+                "c4s": c4s_line, "earlyfusion": ef_line}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if gather_parity is False:
+        raise SystemExit("gather parity FAILED: a rank's re-scored sample differs from the gathered score vector")
 
 
 if __name__ == "__main__":

@@ -20,5 +20,20 @@ def build(force: bool = False) -> str:
     return OUT
 
 
+STUB_SRC = os.path.join(HERE, "abi_stub.c")
+STUB_OUT = os.path.join(HERE, "libacoss_abi_stub.so")
+
+
+def build_stub(force: bool = False) -> str:
+    """CPU stand-in of four C-ABI entry points over the oracle (tests/test_reference_class.py only; see abi_stub.c)."""
+    if (not force and os.path.exists(STUB_OUT)
+            and os.path.getmtime(STUB_OUT) >= max(os.path.getmtime(STUB_SRC), os.path.getmtime(SRC))):
+        return STUB_OUT
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread",
+           "-o", STUB_OUT, STUB_SRC, SRC, "-lm"]
+    subprocess.check_call(cmd)
+    return STUB_OUT
+
+
 if __name__ == "__main__":
     print(build(force=True))
