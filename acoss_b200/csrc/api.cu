@@ -42,7 +42,7 @@ struct acoss_ctx {
     int32_t fx_exp = -1000, nonneg = 0;
     int64_t ws_limit = (int64_t)24 << 30;
     // grow-only scratch
-    Buf pairs, scores, oti, status, crp, rows, cols, thr_q, thr_r, rrot, aa, bb, D, halo, misc, fast, fbmap, dbg;
+    Buf pairs, scores, oti, status, crp, rows, cols, thr_q, thr_r, rrot, aa, bb, D, halo, misc, fast, fbmap, dbg, glive;
     uint32_t *h_flag = nullptr;   // pinned
     uint32_t *h_dbg = nullptr;    // pinned, 32 diagnostic counters
     int64_t stats[8] = {0};
@@ -178,7 +178,7 @@ int acoss_destroy(acoss_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Buf *bufs[] = {&c->pairs, &c->scores, &c->oti, &c->status, &c->crp, &c->rows, &c->cols, &c->thr_q, &c->thr_r,
-                   &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap, &c->dbg,
+                   &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap, &c->dbg, &c->glive,
                    &c->ef_feat[0], &c->ef_feat[1], &c->ef_feat[2], &c->ef_sq[0], &c->ef_sq[1], &c->ef_cmed, &c->ef_off,
                    &c->ef_csm, &c->ef_stat, &c->ef_shapes, &c->ef_nn, &c->ef_csmoff, &c->ef_oti, &c->ef_pairs,
                    &c->ef_scores, &c->ef_bits, &c->ef_bitoff, &c->ef_stage};
@@ -423,6 +423,8 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     TRY(ensure(c->bb, (size_t)ex_slots * g.max_cols * 4));
     TRY(ensure(c->D, (size_t)ex_slots * g.max_rows * ldd * 4));
     if (fast) TRY(ensure(c->fast, (size_t)slots * fast_slot + 4096));
+    const uint32_t gcap = k2_fast_sparse_cap(slots);
+    if (fast) TRY(ensure(c->glive, ((size_t)gcap + 16) * 4));
     ExactScratch sc;
     sc.rrot = (float *)c->rrot.p; sc.aa = (float *)c->aa.p; sc.bb = (float *)c->bb.p; sc.D = (float *)c->D.p;
     sc.ldd = ldd; sc.slots = (int32_t)ex_slots;
@@ -438,7 +440,7 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
             CtxKernelTimer kt(c);
             TRY(launch_k2_fast(ts, pairs_dev, (const int32_t *)c->oti.p, first, n, *p, g, c->fast.p, fast_slot,
                                (uint32_t *)c->crp.p, (float *)c->thr_q.p, (float *)c->thr_r.p, status, (uint32_t *)c->dbg.p, st, &launches,
-                               c->profiling ? &kt : nullptr));
+                               c->profiling ? &kt : nullptr, (uint32_t *)c->glive.p, gcap));
             // exact fallback for pairs the fast path flagged: compact their slot ids, re-run in groups
             TRY(ensure(c->fbmap, (size_t)slots * 4 + 64));
             int nfb = 0;

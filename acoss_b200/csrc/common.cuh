@@ -74,7 +74,9 @@ __device__ __forceinline__ double acc_f32prod(double acc, float a, float b) {
 #define K2K_SCATTER 9
 #define K2K_THR 10
 #define K2K_BITS 11
-#define K2K_COUNT 12
+#define K2K_EXACT 12
+#define K2K_FINAL 13
+#define K2K_COUNT 14
 struct KernelTimer {
     virtual void begin(int id) = 0;
     virtual void end(int id) = 0;

@@ -34,7 +34,6 @@ namespace {
 constexpr int M9 = 9;               // frameStackSize handled by this path
 constexpr int HALO = M9 - 1;        // owned columns a strip recomputes (8)
 constexpr int NBIN = 64;            // histogram bins per level (+ one underflow and one overflow row)
-constexpr int SPARSE_CAP = 512;     // live lines per pair and orientation the sparse refinement can take
 constexpr int SBIN = 256;           // bins of the per-line sample histogram (select kernel)
 constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
 constexpr int CAND_CAP = 128;       // candidates per row / column
@@ -43,6 +42,9 @@ constexpr int WPC = 4;              // warps per CTA in the sweep kernels
 constexpr int RCV = 4;              // owned frames per lane (register columns) in the sweep kernels
 #ifndef K2_FFMA2
 #define K2_FFMA2 1                  // 1: packed fma.rn.f32x2 dot products (FFMA2); 0: the same chains as scalar FFMA
+#endif
+#ifndef K2_SPLIT
+#define K2_SPLIT 1                  // FMA chains per (even, odd) half of a dot product: 1 = six steps each, 2 = two chains of three
 #endif
 #ifndef K2_MINB
 #define K2_MINB 3                   // CTAs per SM the sweep kernels are compiled for (register cap 168 at 3, 255 at 2)
@@ -61,7 +63,7 @@ struct PairHdr {                    // per-slot header written by fast_prep_kern
 struct FastLayout {
     size_t slot_bytes;
     size_t off_hdr, off_rrot, off_aaf, off_bbf, off_aai, off_bbi, off_lo, off_w, off_cb, off_sh, off_cnt,
-        off_cand, off_candz, off_zin, off_zout, off_rowpack, off_pool, off_pcnt, off_samp_r, off_samp_c, off_live, off_nlive,
+        off_cand, off_candz, off_zin, off_zout, off_rowpack, off_pool, off_pcnt, off_samp_r, off_samp_c,
         off_lsel, off_wlist, off_wcnt, off_win;
     int max_rows, max_cols, max_frames, lines, pool_cap;
     int slog;                           // log2 of the diagonal sampling stride S
@@ -120,8 +122,6 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.nst_c = ((g.max_rows - 1) >> L.slog) + 1;
     L.off_samp_r = take((size_t)L.nst_r * g.max_rows * 4);      // [t = j / S][i]
     L.off_samp_c = take((size_t)L.nst_c * g.max_cols * 4);      // [t = i / S][j]
-    L.off_live = take((size_t)2 * SPARSE_CAP * 4);              // [side][SPARSE_CAP] lines still live after the dense level
-    L.off_nlive = take(8);
     L.off_lsel = take((size_t)L.lines * 20);                    // LineSel per line
     L.off_wlist = take((size_t)L.lines * 4 * 8);                // WinCell list: WFLAT_PER_LINE entries per line
     L.off_wcnt = take(4);
@@ -158,14 +158,20 @@ __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
     return d;
 }
 // raw bits of the two half chains, summed (= quantised 2<x, y> + 2 * bits(magic)); x, y: 12 floats each
+constexpr int NMAGIC = 2 * K2_SPLIT;                // magic offsets inside one quantised dot product
 __device__ __forceinline__ int dot_fx(const float (&x)[NBINS], const float (&y)[NBINS], float magic) {
-    float ae = magic, ao = magic;
+    int r = 0;
 #pragma unroll
-    for (int b = 0; b < NBINS; b += 2) {
-        ae = __fmaf_rn(x[b], y[b], ae);
-        ao = __fmaf_rn(x[b + 1], y[b + 1], ao);
+    for (int c = 0; c < K2_SPLIT; ++c) {           // bins [c * 12 / SPLIT, (c + 1) * 12 / SPLIT): one (even, odd) chain pair
+        float ae = magic, ao = magic;
+#pragma unroll
+        for (int b = c * (NBINS / K2_SPLIT); b < (c + 1) * (NBINS / K2_SPLIT); b += 2) {
+            ae = __fmaf_rn(x[b], y[b], ae);
+            ao = __fmaf_rn(x[b + 1], y[b + 1], ao);
+        }
+        r += __float_as_int(ae) + __float_as_int(ao);
     }
-    return __float_as_int(ae) + __float_as_int(ao);
+    return r;
 }
 __device__ __forceinline__ void load_frame(const float *__restrict__ p, float (&x)[NBINS], float scale) {
     const float4 *q = reinterpret_cast<const float4 *>(p);
@@ -199,7 +205,6 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
     }
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     for (int i = threadIdx.x; i < L.lines; i += blockDim.x) cnt[i] = 0u;
-    if (threadIdx.x < 2) slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive)[threadIdx.x] = 0u;
     if (threadIdx.x == 0) { *slot_ptr<uint32_t>(scratch, L, slot, L.off_pcnt) = 0u; *slot_ptr<uint32_t>(scratch, L, slot, L.off_wcnt) = 0u; }
     __syncthreads();
     float *aaf = slot_ptr<float>(scratch, L, slot, L.off_aaf), *bbf = slot_ptr<float>(scratch, L, slot, L.off_bbf);
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(128) fast_sample_kernel(TrackSet ts, const int
     float x[NBINS];
     load_frame(Qf + (int64_t)min(i, nq - 1) * NBINS, x, 2.f);
     const int aa = iok ? aai[i] : 0;
-    const int mbits2 = 2 * __float_as_int(magic);
+    const int mbits2 = NMAGIC * __float_as_int(magic);
 #pragma unroll
     for (int kd = 0; kd < SKD; ++kd) {
         const int d = (u0 + kd) << slog;
@@ -409,11 +414,11 @@ struct Sweep {
     unsigned okm[RC];                             // lane has a left neighbour holding column c-9
     unsigned nz0;                                 // all ones except on lane 0
     u64 magic2;                                   // (magic, magic)
-    int mbits2;                                   // 2 * bits(magic) (mod 2^32)
+    int mbits2;                                   // NMAGIC * bits(magic) (mod 2^32): the offsets inside one quantised e
 
     __device__ __forceinline__ void init(const float *__restrict__ Y, int nY, int cb, int lane, float magic_) {
         magic2 = pack2(magic_, magic_);
-        mbits2 = 2 * __float_as_int(magic_);
+        mbits2 = NMAGIC * __float_as_int(magic_);
         nz0 = lane ? 0xffffffffu : 0u;
 #pragma unroll
         for (int k = 0; k < RC; ++k) {
@@ -435,39 +440,49 @@ struct Sweep {
     // frame-level dot products of one streamed frame (six (even, odd) pairs) with the lane's RC owned frames
     __device__ __forceinline__ void dot(const ulonglong2 &x0, const ulonglong2 &x1, const ulonglong2 &x2, int (&eb)[RC]) const {
 #if K2_FFMA2
-        u64 acc[RC];
+        const u64 xs[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
+        u64 acc[K2_SPLIT][RC];
+        constexpr int PER = 6 / K2_SPLIT;             // packed steps per chain
 #pragma unroll
-        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x0.x, y[k][0], magic2);
+        for (int t = 0; t < PER; ++t)
 #pragma unroll
-        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x0.y, y[k][1], acc[k]);
+            for (int c = 0; c < K2_SPLIT; ++c)
 #pragma unroll
-        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x1.x, y[k][2], acc[k]);
+                for (int k = 0; k < RC; ++k)
+                    acc[c][k] = ffma2(xs[c * PER + t], y[k][c * PER + t], t == 0 ? magic2 : acc[c][k]);
 #pragma unroll
-        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x1.y, y[k][3], acc[k]);
+        for (int k = 0; k < RC; ++k) {
+            int e = 0;
 #pragma unroll
-        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x2.x, y[k][4], acc[k]);
-#pragma unroll
-        for (int k = 0; k < RC; ++k) acc[k] = ffma2(x2.y, y[k][5], acc[k]);
-#pragma unroll
-        for (int k = 0; k < RC; ++k) eb[k] = (int)(unsigned)(acc[k] & 0xffffffffu) + (int)(unsigned)(acc[k] >> 32);
+            for (int c = 0; c < K2_SPLIT; ++c) e += (int)(unsigned)(acc[c][k] & 0xffffffffu) + (int)(unsigned)(acc[c][k] >> 32);
+            eb[k] = e;
+        }
 #else
-        // the same two chains per column as scalar FFMA (bit-identical halves)
+        // the same chains per column as scalar FFMA (bit-identical halves)
         const u64 xs[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
         const float mg = __uint_as_float((unsigned)(magic2 & 0xffffffffu));
-        float ae[RC], ao[RC];
+        constexpr int PER = 6 / K2_SPLIT;
+        float ae[K2_SPLIT][RC], ao[K2_SPLIT][RC];
 #pragma unroll
-        for (int k = 0; k < RC; ++k) { ae[k] = mg; ao[k] = mg; }
+        for (int t = 0; t < PER; ++t)
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            const float xe = __uint_as_float((unsigned)(xs[b] & 0xffffffffu)), xo = __uint_as_float((unsigned)(xs[b] >> 32));
+            for (int c = 0; c < K2_SPLIT; ++c) {
+                const u64 xv = xs[c * PER + t];
+                const float xe = __uint_as_float((unsigned)(xv & 0xffffffffu)), xo = __uint_as_float((unsigned)(xv >> 32));
 #pragma unroll
-            for (int k = 0; k < RC; ++k) {
-                ae[k] = __fmaf_rn(xe, __uint_as_float((unsigned)(y[k][b] & 0xffffffffu)), ae[k]);
-                ao[k] = __fmaf_rn(xo, __uint_as_float((unsigned)(y[k][b] >> 32)), ao[k]);
+                for (int k = 0; k < RC; ++k) {
+                    const u64 yv = y[k][c * PER + t];
+                    ae[c][k] = __fmaf_rn(xe, __uint_as_float((unsigned)(yv & 0xffffffffu)), t == 0 ? mg : ae[c][k]);
+                    ao[c][k] = __fmaf_rn(xo, __uint_as_float((unsigned)(yv >> 32)), t == 0 ? mg : ao[c][k]);
+                }
             }
-        }
 #pragma unroll
-        for (int k = 0; k < RC; ++k) eb[k] = __float_as_int(ae[k]) + __float_as_int(ao[k]);
+        for (int k = 0; k < RC; ++k) {
+            int e = 0;
+#pragma unroll
+            for (int c = 0; c < K2_SPLIT; ++c) e += __float_as_int(ae[c][k]) + __float_as_int(ao[c][k]);
+            eb[k] = e;
+        }
 #endif
     }
 
@@ -669,7 +684,8 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_hist_kernel(TrackSet t
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
                                                              uint32_t *__restrict__ status, uint32_t *__restrict__ dbg,
-                                                             int min_live, int final_level) {
+                                                             int min_live, int final_level, uint32_t *__restrict__ glive,
+                                                             uint32_t gcap) {
     extern __shared__ uint32_t s_hist[];                      // [WPC][NBIN + 2][RC / 2][32], two 16-bit counters per word
     using SW = Sweep<RC>;
     static_assert(RC % 2 == 0, "histogram packing needs an even number of register columns");
@@ -719,16 +735,17 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_hist_kernel(TrackSet t
 #pragma unroll
     for (int kk = 0; kk < RC; ++kk) n_live += valid[kk] ? 1 : 0;
     const int side = (ORIENT == 0) ? 1 : 0;
-    uint32_t *nlive = slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive) + side;
-    int32_t *live = slot_ptr<int32_t>(scratch, L, slot, L.off_live) + side * SPARSE_CAP;
+    // a line the sparse refinement has to finish goes to the CALL-wide list (lines of all pairs share its warps)
+    auto to_sparse = [&](int line) {
+        const unsigned pos = atomicAdd(glive, 1u);
+        if (pos < gcap) glive[1 + pos] = ((uint32_t)slot << 16) | ((uint32_t)side << 15) | (uint32_t)line;
+        else atomicOr(&status[k], PAIR_ST_FALLBACK | 8u);     // reason 8: too many crowded lines in this call
+    };
     if (__reduce_add_sync(0xffffffffu, n_live) < min_live) {
         // too few live lines to pay for a dense sweep of the strip: they go to the sparse refinement as they are
 #pragma unroll
-        for (int kk = 0; kk < RC; ++kk) {
-            if (!valid[kk]) continue;
-            const unsigned pos = atomicAdd(nlive, 1u);
-            if (pos < SPARSE_CAP) live[pos] = cb + RC * lane + kk - HALO;
-        }
+        for (int kk = 0; kk < RC; ++kk)
+            if (valid[kk]) to_sparse(cb + RC * lane + kk - HALO);
         return;
     }
     SW sw;
@@ -773,10 +790,7 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_hist_kernel(TrackSet t
             int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
             rowpack[j] = make_int4(yn[j], br.lo - 2 * EPS, br.w + 4 * EPS, 0);
         }
-        if (!br.done && final_level) {                        // the sparse level refines it
-            const unsigned pos = atomicAdd(nlive, 1u);
-            if (pos < SPARSE_CAP) live[pos] = j;
-        }
+        if (!br.done && final_level) to_sparse(j);            // the sparse level refines it
     }
     n_live = __reduce_add_sync(0xffffffffu, n_live);
     n_miss = __reduce_add_sync(0xffffffffu, n_miss);
@@ -812,20 +826,18 @@ __device__ __forceinline__ void sparse_step(const float (&y)[M9][NBINS], int (&a
 __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                                   int64_t first, int n, FastLayout L,
                                                                   char *__restrict__ scratch, float magic,
-                                                                  uint32_t *__restrict__ status, uint32_t *__restrict__ dbg) {
+                                                                  uint32_t *__restrict__ status, uint32_t *__restrict__ dbg,
+                                                                  const uint32_t *__restrict__ glive, uint32_t gcap) {
     __shared__ uint32_t s_sp[WPC][NBIN + 2][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int CHUNKS = SPARSE_CAP / 32;
-    const int64_t task = (int64_t)blockIdx.x * WPC + warp;
-    const int slot = (int)(task / (2 * CHUNKS));
-    if (slot >= n) return;
-    const int rem = (int)(task - (int64_t)slot * (2 * CHUNKS));
-    const int side = rem / CHUNKS, chunk = rem - side * CHUNKS;    // side 0: rows (owned = query), 1: columns
-    const uint32_t cnt_all = slot_ptr<uint32_t>(scratch, L, slot, L.off_nlive)[side];
+    const uint32_t cnt = min(glive[0], gcap);
+    const uint32_t e0 = ((uint32_t)blockIdx.x * WPC + warp) * 32u;
+    if (e0 >= cnt) return;
+    // one lane = one line; the 32 lines of a warp may belong to 32 different pairs (everything below is lane-private)
+    bool livel = e0 + lane < cnt;
+    const uint32_t ent = glive[1 + (livel ? e0 + lane : e0)];
+    const int slot = (int)(ent >> 16), side = (int)((ent >> 15) & 1u), j = (int)(ent & 0x7fffu);   // side 0: rows (owned = query)
     const int64_t k = first + slot;
-    if (cnt_all > SPARSE_CAP && chunk == 0 && lane == 0) atomicOr(&status[k], PAIR_ST_FALLBACK | 8u);   // reason 8: too many crowded lines
-    const int cnt = (int)min(cnt_all, (uint32_t)SPARSE_CAP);
-    if (chunk * 32 >= cnt) return;
     const PairHdr *h = slot_ptr<PairHdr>(scratch, L, slot, L.off_hdr);
     const int q = pairs[2 * k];
     const int nY = side ? h->nr : h->nq, nX = side ? h->nq : h->nr;
@@ -839,26 +851,25 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, c
     int32_t *w_a = slot_ptr<int32_t>(scratch, L, slot, L.off_w) + line0;
     int32_t *cb_a = slot_ptr<int32_t>(scratch, L, slot, L.off_cb) + line0;
     int32_t *sh_a = slot_ptr<int32_t>(scratch, L, slot, L.off_sh) + line0;
-    const int li = chunk * 32 + lane;
-    bool livel = li < cnt;
-    const int j = livel ? slot_ptr<int32_t>(scratch, L, slot, L.off_live)[side * SPARSE_CAP + li] : 0;
     // owned window j: frames j .. j+8, pre-doubled (the sweeps double the owned side too)
     float y[M9][NBINS];
 #pragma unroll
     for (int t = 0; t < M9; ++t) load_frame(Y + (int64_t)min(j + t, nY - 1) * NBINS, y[t], 2.f);
-    const int ynj = livel ? yn[j] : 0;
+    const int ynj = yn[j];
     const int fk = h->fk[side], ck = h->ck[side], rlo = h->lo1, rhi = h->hi1;
-    const int mb9 = 2 * M9 * __float_as_int(magic);           // the 18 magic offsets inside a completed sum (mod 2^32)
+    const int mb9 = NMAGIC * M9 * __float_as_int(magic);      // the magic offsets inside a completed sum (mod 2^32)
     uint32_t *hist = &s_sp[warp][0][lane];
-    int lo = livel ? lo_a[j] : 0, sh = livel ? sh_a[j] : 0;
-    if (livel && sh < 0) livel = false;
-    const int nrows = nX - 1;                                 // streamed frames 0 .. nX-2
+    int lo = lo_a[j], sh = sh_a[j];
+    if (sh < 0) livel = false;
+    const int nrows = nX - 1;                                 // this lane's streamed frames 0 .. nX-2
+    const int nrows_w = __reduce_max_sync(0xffffffffu, nrows);
     int n_swept = 0;
     for (int lvl = 0; lvl < SPARSE_LEVELS && __any_sync(0xffffffffu, livel); ++lvl) {
         ++n_swept;
 #pragma unroll 1
         for (int b = 0; b < NBIN + 2; ++b) hist[b * 32] = 0u;
-        const int yrel = livel ? ynj - lo + (1 << sh) : 0x40000000;   // idle lanes land in the overflow bin
+        const int shl = max(sh, 0);
+        const int yrel = livel ? ynj - lo + (1 << shl) : 0x40000000;   // idle lanes land in the overflow bin
         const float *px = X;
         float xc[NBINS];
         load_frame(px, xc, 1.f);
@@ -869,22 +880,22 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, c
         auto step = [&](auto uc) {
             constexpr int U = decltype(uc)::value;
             sparse_step<U>(y, acc, xc, magic);
-            px += NBINS;
+            if (a + 1 < nX) px += NBINS;                      // lanes past the end of their track keep their last frame
             load_frame(px, xc, 1.f);
-            if (a >= HALO) {                                  // row a - 8 is complete (slot (U + 1) % 9)
+            if (a >= HALO && a < nrows) {                     // row a - 8 is complete (slot (U + 1) % 9)
                 const int T = acc[(U + 1) % M9] - mb9;
                 const int zr = __ldg(xn + a - HALO) + yrel - T;
-                const int idx = __vimin_s32_relu(zr >> sh, NBIN + 1);
+                const int idx = __vimin_s32_relu(zr >> shl, NBIN + 1);
                 atomicAdd(&hist[idx * 32], 1u);
             }
             ++a;
         };
 #pragma unroll 1
-        while (a + M9 <= nrows) {
+        while (a + M9 <= nrows_w) {
             step(IC<0>{}); step(IC<1>{}); step(IC<2>{}); step(IC<3>{}); step(IC<4>{});
             step(IC<5>{}); step(IC<6>{}); step(IC<7>{}); step(IC<8>{});
         }
-        const int remr = nrows - a;
+        const int remr = nrows_w - a;
         if (remr > 0) step(IC<0>{});
         if (remr > 1) step(IC<1>{});
         if (remr > 2) step(IC<2>{});
@@ -1481,7 +1492,7 @@ size_t k2_fast_slot_bytes(const SlotGeom &g, int max_frames) { return make_layou
 int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti, int64_t first, int n,
                    const acoss_params &p, const SlotGeom &g, void *scratch, size_t slot_bytes, uint32_t *crp,
                    float *thr_q, float *thr_r, uint32_t *status, uint32_t *dbg, cudaStream_t st, int64_t *launches,
-                   KernelTimer *timer) {
+                   KernelTimer *timer, uint32_t *glive, uint32_t gcap) {
     if (n <= 0) return ACOSS_OK;
     constexpr int RC = RCV;
     const FastLayout L = make_layout(g, ts.max_frames);
@@ -1492,6 +1503,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     const float magic = ldexpf(1.f, ts.fx_exp);
     const double unit = ldexp(1.0, ts.fx_exp - 23);
     const float fx_scale = ldexpf(1.f, 23 - ts.fx_exp);
+    CUDA_TRY(cudaMemsetAsync(glive, 0, 4, st));
     auto tb = [&](int id) { if (timer) timer->begin(id); };
     auto te = [&](int id) { if (timer) timer->end(id); };
     tb(K2K_PREP);
@@ -1534,22 +1546,24 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     // lines (short lines start from the whole item range and need it; ordinary strips skip it at once) and hands
     // every line still live to the sparse refinement
     tb(K2K_HIST_COL);
-    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg, 1, 0);
+    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg, 1, 0, glive, gcap);
     te(K2K_HIST_COL);
     tb(K2K_HIST_ROW);
-    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 4, 1, 0);
+    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 4, 1, 0, glive, gcap);
     te(K2K_HIST_ROW);
     tb(K2K_HIST_COL2);
-    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1);
+    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap);
     te(K2K_HIST_COL2);
     tb(K2K_HIST_ROW2);
-    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1);
+    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap);
     CUDA_TRY(cudaGetLastError());
     te(K2K_HIST_ROW2);
     {
-        const int64_t warps = (int64_t)n * 2 * (SPARSE_CAP / 32);
+        // the crowded lines of ALL pairs of the call, one lane each (warps that find nothing past the list's end return)
+        const int64_t warps = ((int64_t)gcap + 31) / 32;
         tb(K2K_SPARSE);
-        fast_sparse_kernel<<<(unsigned)((warps + WPC - 1) / WPC), 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, magic, status, dbg + 8);
+        fast_sparse_kernel<<<(unsigned)((warps + WPC - 1) / WPC), 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, magic, status, dbg + 8,
+                                                                                     glive, gcap);
         CUDA_TRY(cudaGetLastError());
         te(K2K_SPARSE);
     }
@@ -1568,10 +1582,14 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     te(K2K_SCATTER);
     tb(K2K_THR);
     fast_rank_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(n, L, base);
+    te(K2K_THR);
+    tb(K2K_EXACT);
     fast_exact_kernel<<<dim3((WFLAT_PER_LINE * lines + 255) / 256, n), 256, 0, st>>>(ts, pairs, first, n, L, base, status, dbg);
+    te(K2K_EXACT);
+    tb(K2K_FINAL);
     fast_thr_kernel<<<dim3((lines + 127) / 128, n), 128, 0, st>>>(first, n, L, base, p.integer_guard, unit, thr_q, thr_r, status);
     CUDA_TRY(cudaGetLastError());
-    te(K2K_THR);
+    te(K2K_FINAL);
     tb(K2K_BITS);
     fast_resolve_bits_kernel<<<dim3((lines * 16 + 255) / 256, n), 256, 0, st>>>(ts, pairs, first, n, L, base, thr_q, thr_r, crp,
                                                                                       g.words, g.crp_words, status, dbg);

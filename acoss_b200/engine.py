@@ -198,7 +198,7 @@ class Engine:
         return dict(k1_oti=float(ms[0]), k2_crp=float(ms[1]), k3_dp=float(ms[2]), k2_emit=float(ms[3]))
 
     K2_KERNELS = ("prep", "sample", "select", "hist_col", "hist_row", "hist_col2", "hist_row2", "sparse", "emit",
-                  "scatter", "thr", "bits")
+                  "scatter", "rank", "bits", "exact", "thr")
 
     def kernel_ms(self) -> dict:
         """Accumulated CUDA-event milliseconds of every kernel of the fast K2 path since set_profiling(True)."""

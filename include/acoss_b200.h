@@ -204,8 +204,9 @@ int acoss_set_profiling(acoss_ctx *ctx, int on);
 int acoss_stage_ms(acoss_ctx *ctx, double ms[4]);
 /* Device milliseconds of every kernel of the fast K2 path since acoss_set_profiling(ctx, 1) (CUDA events around each
  * launch): [0] prep, [1] diagonal sampler, [2] sample selection, [3] / [4] dense histogram sweep columns / rows,
- * [5] / [6] the gated second level, [7] sparse refinement, [8] emit sweep, [9] candidate scatter, [10] thresholds
- * (exact order statistics), [11] candidate bits; [12..15] reserved (0). */
+ * [5] / [6] the gated second level, [7] sparse refinement, [8] emit sweep, [9] candidate scatter, [10] candidate
+ * ranking (z order statistics, window cells), [11] candidate bits, [12] exact evaluation of the window cells,
+ * [13] thresholds; [14..15] reserved (0). */
 int acoss_kernel_ms(acoss_ctx *ctx, double ms[16]);
 
 #ifdef __cplusplus
