@@ -46,6 +46,19 @@ struct acoss_ctx {
     uint32_t *h_flag = nullptr;   // pinned
     uint32_t *h_dbg = nullptr;    // pinned, 32 diagnostic counters
     int64_t stats[8] = {0};
+    // deferred exact fallback of the last asynchronous call (pairs the fast CRP path flagged): the first
+    // FB_ROUNDS * fb_slots of them are re-scored inside the call's own stream work; if more were flagged, acoss_sync()
+    // scores the rest
+    struct PendingFb {
+        int active = 0;
+        const int32_t *pairs_dev = nullptr;
+        float *scores_dev = nullptr, *scores2_dev = nullptr;
+        acoss_params p;
+        SlotGeom g;
+        int64_t ldd = 0, halo_pitch = 0, K = 0;
+        int fb_slots = 0, done = 0;
+    } fb;
+    Buf fbtmp;
     int pending_status_check = 0;
     int stats_reason_pending = 0;
     int64_t pending_pairs = 0;
@@ -178,7 +191,7 @@ int acoss_destroy(acoss_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Buf *bufs[] = {&c->pairs, &c->scores, &c->oti, &c->status, &c->crp, &c->rows, &c->cols, &c->thr_q, &c->thr_r,
-                   &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap, &c->dbg, &c->glive,
+                   &c->rrot, &c->aa, &c->bb, &c->D, &c->halo, &c->misc, &c->fast, &c->fbmap, &c->dbg, &c->glive, &c->fbtmp,
                    &c->ef_feat[0], &c->ef_feat[1], &c->ef_feat[2], &c->ef_sq[0], &c->ef_sq[1], &c->ef_cmed, &c->ef_off,
                    &c->ef_csm, &c->ef_stat, &c->ef_shapes, &c->ef_nn, &c->ef_csmoff, &c->ef_oti, &c->ef_pairs,
                    &c->ef_scores, &c->ef_bits, &c->ef_bitoff, &c->ef_stage};
@@ -365,6 +378,41 @@ struct DumpOut {
     float *thr_q = nullptr, *thr_r = nullptr;
 };
 
+constexpr int FB_ROUNDS = 4;      // deferred exact-fallback rounds issued without knowing how many pairs were flagged
+
+// One round of the deferred exact fallback: the pairs map[0 .. nslots) (absolute pair indices, negative = unused)
+// are re-scored by the exact CRP path in scratch slots 0 .. nslots-1 and their scores overwrite scores_dev[map[.]].
+static int fallback_round(acoss_ctx *c, const TrackSet &ts, const int32_t *pairs_dev, const acoss_params *p, const SlotGeom &g,
+                          int64_t ldd, int64_t halo_pitch, const int32_t *map_dev, int nslots, float *scores_dev,
+                          float *scores2_dev, int64_t *launches) {
+    cudaStream_t st = c->stream;
+    ExactScratch sc;
+    sc.rrot = (float *)c->rrot.p; sc.aa = (float *)c->aa.p; sc.bb = (float *)c->bb.p; sc.D = (float *)c->D.p;
+    sc.ldd = ldd; sc.slots = nslots;
+    uint32_t *status = (uint32_t *)c->status.p;
+    const int incr = win_incr(p);
+    TRY(launch_k2_exact(ts, pairs_dev, (const int32_t *)c->oti.p, 0, nslots, *p, g, sc, (uint32_t *)c->crp.p, (float *)c->thr_q.p,
+                        (float *)c->thr_r.p, status, map_dev, st, launches, true));
+    TRY(launch_pair_geometry_map(ts, pairs_dev, map_dev, nslots, incr, (int32_t *)c->rows.p, (int32_t *)c->cols.p, st));
+    float *tmp = (float *)c->fbtmp.p;
+    if (!scores2_dev && p->align == ACOSS_ALIGN_SW)
+        TRY(launch_sw_trim((uint32_t *)c->crp.p, g.crp_words, g.words, (int32_t *)c->rows.p, (int32_t *)c->cols.p, nslots, st));
+    TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p, (const int32_t *)c->cols.p,
+                       nslots, g.max_cols, scores2_dev ? ACOSS_ALIGN_QMAX : p->align, p->gamma_o, p->gamma_e, tmp,
+                       (uint32_t *)c->halo.p, halo_pitch, st, launches));
+    if (p->f5_asymmetric) TRY(launch_score_asymmetric(tmp, (const int32_t *)c->cols.p, nslots, st));
+    TRY(launch_scatter_scores(tmp, map_dev, nslots, scores_dev, st));
+    if (scores2_dev) {
+        TRY(launch_dp_bits((const uint32_t *)c->crp.p, g.crp_words, g.words, (const int32_t *)c->rows.p, (const int32_t *)c->cols.p,
+                           nslots, g.max_cols, ACOSS_ALIGN_DMAX, p->gamma_o, p->gamma_e, tmp, (uint32_t *)c->halo.p, halo_pitch, st,
+                           launches));
+        if (p->f5_asymmetric) TRY(launch_score_asymmetric(tmp, (const int32_t *)c->cols.p, nslots, st));
+        TRY(launch_scatter_scores(tmp, map_dev, nslots, scores2_dev, st));
+    }
+    if (launches) *launches += 3;
+    return ACOSS_OK;
+}
+
 // Core pipeline.  pairs_dev / scores_dev are device pointers.
 // scores2_dev (optional): Dmax scores of the same CRPs (ChenFusion), scores_dev then holds Qmax.
 static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const acoss_params *p, float *scores_dev,
@@ -412,12 +460,16 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     const int fb_slots = fast ? (int)std::max<int64_t>(1, std::min<int64_t>(16, ((int64_t)2 << 30) / (int64_t)exact_slot)) : 0;
     const int64_t ex_slots = fast ? fb_slots : slots;
 
-    TRY(ensure(c->crp, (size_t)slots * g.crp_words * 4));
-    TRY(ensure(c->rows, (size_t)slots * 4));
-    TRY(ensure(c->cols, (size_t)slots * 4));
-    TRY(ensure(c->thr_q, (size_t)slots * g.max_rows * 4));
-    TRY(ensure(c->thr_r, (size_t)slots * g.max_cols * 4));
-    TRY(ensure(c->halo, (size_t)slots * 2 * halo_pitch * 16));
+    const int64_t oslots = std::max<int64_t>(slots, fb_slots);   // the deferred fallback rounds reuse these buffers
+    TRY(ensure(c->crp, (size_t)oslots * g.crp_words * 4));
+    TRY(ensure(c->rows, (size_t)oslots * 4));
+    TRY(ensure(c->cols, (size_t)oslots * 4));
+    TRY(ensure(c->thr_q, (size_t)oslots * g.max_rows * 4));
+    TRY(ensure(c->thr_r, (size_t)oslots * g.max_cols * 4));
+    TRY(ensure(c->halo, (size_t)oslots * 2 * halo_pitch * 16));
+    TRY(ensure(c->fbtmp, (size_t)std::max(fb_slots, 1) * 4 + 64));
+    const bool defer = fast && (dump == nullptr);               // single-pair dumps resolve their fallback at once
+    c->fb.active = 0;
     TRY(ensure(c->rrot, (size_t)ex_slots * c->max_frames * NBINS * 4));
     TRY(ensure(c->aa, (size_t)ex_slots * g.max_rows * 4));
     TRY(ensure(c->bb, (size_t)ex_slots * g.max_cols * 4));
@@ -441,10 +493,13 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
             TRY(launch_k2_fast(ts, pairs_dev, (const int32_t *)c->oti.p, first, n, *p, g, c->fast.p, fast_slot,
                                (uint32_t *)c->crp.p, (float *)c->thr_q.p, (float *)c->thr_r.p, status, (uint32_t *)c->dbg.p, st, &launches,
                                c->profiling ? &kt : nullptr, (uint32_t *)c->glive.p, gcap));
-            // exact fallback for pairs the fast path flagged: compact their slot ids, re-run in groups
-            TRY(ensure(c->fbmap, (size_t)slots * 4 + 64));
+            // exact fallback for pairs the fast path flagged.  Batched calls defer it to the end of the call (no host
+            // synchronisation between chunks); a debug dump compacts the flagged slots and re-runs them at once
             int nfb = 0;
-            TRY(k2_fast_collect_fallback(status, first, n, (int32_t *)c->fbmap.p, (int32_t *)((char *)c->misc.p + 128), &nfb, st));
+            if (!defer) {
+                TRY(ensure(c->fbmap, (size_t)slots * 4 + 64));
+                TRY(k2_fast_collect_fallback(status, first, n, (int32_t *)c->fbmap.p, (int32_t *)((char *)c->misc.p + 128), &nfb, st));
+            }
             if (nfb > 0) {
                 c->stats[1] += nfb;
                 for (int b0 = 0; b0 < nfb; b0 += fb_slots) {
@@ -495,6 +550,25 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
         }
         t3.stop();
     }
+    if (defer) {
+        // Deferred exact fallback: compact the flagged pairs of the whole call on the device, re-score the first
+        // FB_ROUNDS * fb_slots of them right here (kernels skip unused map entries, so no count is needed on the
+        // host); the count travels to the host with the status word and acoss_sync() finishes any remainder.
+        TRY(ensure(c->fbmap, (size_t)(K + FB_ROUNDS * fb_slots) * 4 + 64));
+        int32_t *map = (int32_t *)c->fbmap.p;
+        CUDA_TRY(cudaMemsetAsync(map, 0xff, (size_t)(K + FB_ROUNDS * fb_slots) * 4, st));
+        TRY(k2_fast_collect_fallback(status, 0, (int)K, map, (int32_t *)((char *)c->misc.p + 128), nullptr, st));
+        ++launches;
+        StageTimer t4(c, 1);
+        for (int r = 0; r < FB_ROUNDS; ++r)
+            TRY(fallback_round(c, ts, pairs_dev, p, g, ldd, halo_pitch, map + r * fb_slots, fb_slots, scores_dev, scores2_dev,
+                               &launches));
+        t4.stop();
+        CUDA_TRY(cudaMemcpyAsync(c->h_flag + 2, (char *)c->misc.p + 128, 4, cudaMemcpyDeviceToHost, st));
+        c->fb.active = 1; c->fb.pairs_dev = pairs_dev; c->fb.scores_dev = scores_dev; c->fb.scores2_dev = scores2_dev;
+        c->fb.p = *p; c->fb.g = g; c->fb.ldd = ldd; c->fb.halo_pitch = halo_pitch; c->fb.K = K; c->fb.fb_slots = fb_slots;
+        c->fb.done = FB_ROUNDS * fb_slots;
+    }
     // fold per-pair status into one word; read back at sync time
     or_reduce_kernel<<<148, 256, 0, st>>>(status, K, (uint32_t *)c->misc.p);
     CUDA_TRY(cudaGetLastError());
@@ -509,9 +583,36 @@ static int run_pairs(acoss_ctx *c, const int32_t *pairs_dev, int64_t K, const ac
     return ACOSS_OK;
 }
 
+// waits for the stream and completes the deferred exact fallback of the last asynchronous call
+static int finish_pending(acoss_ctx *c) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->fb.active) {
+        // the asynchronous call re-scored the first fb.done flagged pairs itself; the (rare) remainder is scored here
+        c->fb.active = 0;
+        const int nfb = (int)c->h_flag[2];
+        c->stats[1] = nfb;
+        if (nfb > c->fb.done) {
+            const TrackSet ts = track_set(c);
+            int64_t launches = 0;
+            const int32_t *map = (const int32_t *)c->fbmap.p;
+            for (int b0 = c->fb.done; b0 < nfb; b0 += c->fb.fb_slots)
+                TRY(fallback_round(c, ts, c->fb.pairs_dev, &c->fb.p, c->fb.g, c->fb.ldd, c->fb.halo_pitch, map + b0,
+                                   c->fb.fb_slots, c->fb.scores_dev, c->fb.scores2_dev, &launches));
+            // the remainder may have raised the NaN status of its pairs: fold the status words again
+            CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, c->stream));
+            or_reduce_kernel<<<148, 256, 0, c->stream>>>((const uint32_t *)c->status.p, c->fb.K, (uint32_t *)c->misc.p);
+            CUDA_TRY(cudaMemcpyAsync(c->h_flag, c->misc.p, 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            c->stats[2] += launches;
+        }
+    }
+    return ACOSS_OK;
+}
+
 int acoss_sync(acoss_ctx *c) {
     if (!c) { acoss_set_error("NULL context"); return ACOSS_E_INVALID; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(finish_pending(c));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     fold_spans(c);
     if (c->pending_status_check) {
@@ -540,6 +641,7 @@ int acoss_score_pairs(acoss_ctx *c, const int32_t *pairs, int64_t K, const acoss
     TRY(ensure(c->scores, (size_t)K * 4));
     CUDA_TRY(cudaMemcpyAsync(c->pairs.p, pairs, (size_t)K * 8, cudaMemcpyHostToDevice, c->stream));
     TRY(run_pairs(c, (const int32_t *)c->pairs.p, K, p, (float *)c->scores.p, nullptr));
+    TRY(finish_pending(c));                                    // every flagged pair is re-scored before the read-back
     CUDA_TRY(cudaMemcpyAsync(scores, c->scores.p, (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
     return acoss_sync(c);
 }
@@ -557,6 +659,7 @@ int acoss_score_pairs_chen(acoss_ctx *c, const int32_t *pairs, int64_t K, const 
     acoss_params pp = *p;
     pp.align = ACOSS_ALIGN_QMAX;
     TRY(run_pairs(c, (const int32_t *)c->pairs.p, K, &pp, (float *)c->scores.p, nullptr, (float *)c->scores.p + K));
+    TRY(finish_pending(c));
     CUDA_TRY(cudaMemcpyAsync(qmax_scores, c->scores.p, (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(dmax_scores, (float *)c->scores.p + K, (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
     return acoss_sync(c);

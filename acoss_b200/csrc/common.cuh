@@ -112,7 +112,7 @@ struct ExactScratch {
 int launch_k2_exact(const TrackSet &ts, const int32_t *pairs, const int32_t *oti, int64_t first, int n,
                     const acoss_params &p, const SlotGeom &g, const ExactScratch &sc,
                     uint32_t *crp, float *thr_q, float *thr_r, uint32_t *status,
-                    const int32_t *slot_pair_map, cudaStream_t st, int64_t *launches);
+                    const int32_t *slot_pair_map, cudaStream_t st, int64_t *launches, bool out_by_slot = false);
 
 // K3: alignment DP over bit-packed matrices.  rows[k], cols[k] give the DP matrix of slot k.
 int launch_dp_bits(const uint32_t *bits, int64_t slot_words, int words_per_row, const int32_t *rows,
@@ -124,6 +124,11 @@ int launch_pair_geometry(const TrackSet &ts, const int32_t *pairs, int64_t first
                          int32_t *rows, int32_t *cols, cudaStream_t st);
 // F5 switch: scores[k] = sqrtf(cols[k]) / scores[k] (essentia distanceType 'asymmetric', App. A6)
 int launch_score_asymmetric(float *scores, const int32_t *cols, int n, cudaStream_t st);
+// the same for mapped pairs: slot k scores pair map[k]; map[k] < 0 -> rows = cols = 0 (the DP returns at once)
+int launch_pair_geometry_map(const TrackSet &ts, const int32_t *pairs, const int32_t *map, int n, int incr,
+                             int32_t *rows, int32_t *cols, cudaStream_t st);
+// dst[map[k]] = src[k] for map[k] >= 0
+int launch_scatter_scores(const float *src, const int32_t *map, int n, float *dst, cudaStream_t st);
 int launch_sw_trim(uint32_t *bits, int64_t slot_words, int words_per_row, int32_t *rows, int32_t *cols, int n,
                    cudaStream_t st);
 int launch_pack_bytes(const uint8_t *mats, const int64_t *offsets, const int32_t *shapes, int n,

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) exact_prep_kernel(TrackSet ts, const int3
                                                          float *__restrict__ bb_all) {
     const int slot = blockIdx.x;
     const int64_t k = slot_map ? slot_map[slot] : first + slot;
+    if (k < 0) return;                                        // unused entry of a fallback map
     const int q = pairs[2 * k], r = pairs[2 * k + 1], s = oti[k] % NBINS;
     const int nq = (int)(ts.offsets[q + 1] - ts.offsets[q]), nr = (int)(ts.offsets[r + 1] - ts.offsets[r]);
     const int M = nq - incr, N = nr - incr;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) exact_dist_kernel(TrackSet ts, const int3
     extern __shared__ float smem[];
     const int slot = blockIdx.z;
     const int64_t k = slot_map ? slot_map[slot] : first + slot;
+    if (k < 0) return;
     const int q = pairs[2 * k], r = pairs[2 * k + 1];
     const int nq = (int)(ts.offsets[q + 1] - ts.offsets[q]), nr = (int)(ts.offsets[r + 1] - ts.offsets[r]);
     const int M = nq - incr, N = nr - incr;
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(256) exact_select_kernel(TrackSet ts, const in
     __shared__ unsigned s_prefix, s_k, s_cnt_le, s_min_gt;
     const int slot = blockIdx.y;
     const int64_t k = slot_map ? slot_map[slot] : first + slot;
+    if (k < 0) return;
+    const int64_t oslot = out_base < 0 ? slot : k - out_base;  // out_base < 0: outputs go to the scratch slot itself
     const int q = pairs[2 * k], r = pairs[2 * k + 1];
     const int M = (int)(ts.offsets[q + 1] - ts.offsets[q]) - incr, N = (int)(ts.offsets[r + 1] - ts.offsets[r]) - incr;
     const int line = blockIdx.x;
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(256) exact_select_kernel(TrackSet ts, const in
     if (threadIdx.x == 0) {
         const unsigned vck = ((int)s_cnt_le >= ick + 1) ? vfk : s_min_gt;
         const float thr = essentia_percentile(__uint_as_float(vfk), __uint_as_float(vck), kf, fk, ck, guard);
-        thr_all[(k - out_base) * (COLS ? max_cols : max_rows) + line] = thr;
+        thr_all[oslot * (COLS ? max_cols : max_rows) + line] = thr;
     }
 }
 
@@ -215,6 +219,8 @@ __global__ void __launch_bounds__(256) exact_emit_kernel(TrackSet ts, const int3
                                                          uint32_t *__restrict__ crp_all) {
     const int slot = blockIdx.z;
     const int64_t k = slot_map ? slot_map[slot] : first + slot;
+    if (k < 0) return;
+    const int64_t oslot = out_base < 0 ? slot : k - out_base;
     const int q = pairs[2 * k], r = pairs[2 * k + 1];
     const int M = (int)(ts.offsets[q + 1] - ts.offsets[q]) - incr, N = (int)(ts.offsets[r + 1] - ts.offsets[r]) - incr;
     const int i = blockIdx.y;
@@ -225,21 +231,22 @@ __global__ void __launch_bounds__(256) exact_emit_kernel(TrackSet ts, const int3
     bool bit = false;
     if (j < N) {
         const float d = D_all[((int64_t)slot * max_rows + i) * ldd + j];
-        const float tq = thr_q_all[(k - out_base) * max_rows + i], tr = thr_r_all[(k - out_base) * max_cols + j];
+        const float tq = thr_q_all[oslot * max_rows + i], tr = thr_r_all[oslot * max_cols + j];
         const float xq = __fsub_rn(tq, d), xr = __fsub_rn(tr, d);        // heaviside arguments (F2)
         bit = strict ? (xq > 0.f && xr > 0.f) : (xq >= 0.f && xr >= 0.f);
     }
     const unsigned word = __ballot_sync(0xffffffffu, bit);
-    if (lane == 0) crp_all[(k - out_base) * crp_words + (int64_t)i * words + w] = word;
+    if (lane == 0) crp_all[oslot * crp_words + (int64_t)i * words + w] = word;
 }
 
 int launch_k2_exact(const TrackSet &ts, const int32_t *pairs, const int32_t *oti, int64_t first, int n,
                     const acoss_params &p, const SlotGeom &g, const ExactScratch &sc, uint32_t *crp,
                     float *thr_q, float *thr_r, uint32_t *status, const int32_t *slot_map, cudaStream_t st,
-                    int64_t *launches) {
-    // scratch slot = blockIdx; pair index k = slot_map ? slot_map[slot] : first + slot; outputs (CRP,
-    // thresholds) land in chunk slot k - first, so a fallback re-run overwrites the pair's own slot.
-    const int64_t out_base = first;
+                    int64_t *launches, bool out_by_slot) {
+    // scratch slot = blockIdx; pair index k = slot_map ? slot_map[slot] : first + slot (negative map entries are
+    // skipped); outputs (CRP, thresholds) land in chunk slot k - first, so a fallback re-run overwrites the pair's
+    // own slot — or, with out_by_slot, in the scratch slot itself (deferred fallback rounds).
+    const int64_t out_base = out_by_slot ? -1 : first;
     if (n <= 0) return ACOSS_OK;
     const int incr = p.f4_keep_last ? (p.m - 1) * p.tau : p.m * p.tau;   // F4
     const float qperc = (float)((double)(p.kappa * 100.f) / 100.);   // App. A4 float32 round trip

@@ -1601,14 +1601,16 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
 
 int k2_fast_collect_fallback(const uint32_t *status, int64_t first, int n, int32_t *map_dev, int32_t *count_dev,
                              int *count_host, cudaStream_t st) {
-    *count_host = 0;
+    if (count_host) *count_host = 0;
     if (n <= 0) return ACOSS_OK;
     CUDA_TRY(cudaMemsetAsync(count_dev, 0, 4, st));
     collect_fallback_kernel<<<(n + 255) / 256, 256, 0, st>>>(status, first, n, map_dev, count_dev);
     CUDA_TRY(cudaGetLastError());
-    int32_t c = 0;
-    CUDA_TRY(cudaMemcpyAsync(&c, count_dev, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    *count_host = c;
+    if (count_host) {                                         // synchronous variant (single-pair debug dumps)
+        int32_t c = 0;
+        CUDA_TRY(cudaMemcpyAsync(&c, count_dev, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        *count_host = c;
+    }
     return ACOSS_OK;
 }

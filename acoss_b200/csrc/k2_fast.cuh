@@ -15,7 +15,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
                    uint32_t *glive, uint32_t gcap); // call-wide list of lines for the sparse level: [0] count, [1..gcap] entries
 // entries the call-wide sparse list should hold for n slots
 inline uint32_t k2_fast_sparse_cap(int64_t slots) { return (uint32_t)(slots * 48 + 4096); }
-// compacts the absolute indices k in [first, first+n) whose status has PAIR_ST_FALLBACK into map_dev;
-// synchronises the stream to return the count
+// compacts the absolute indices k in [first, first+n) whose status has PAIR_ST_FALLBACK into map_dev (count in
+// count_dev); with count_host != NULL it also synchronises the stream to return the count
 int k2_fast_collect_fallback(const uint32_t *status, int64_t first, int n, int32_t *map_dev, int32_t *count_dev,
                              int *count_host, cudaStream_t st);

@@ -555,6 +555,34 @@ int launch_pair_geometry(const TrackSet &ts, const int32_t *pairs, int64_t first
     return ACOSS_OK;
 }
 
+__global__ void pair_geometry_map_kernel(TrackSet ts, const int32_t *__restrict__ pairs, const int32_t *__restrict__ map, int n,
+                                         int incr, int32_t *__restrict__ rows, int32_t *__restrict__ cols) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t m = map[k];
+    if (m < 0) { rows[k] = 0; cols[k] = 0; return; }
+    const int q = pairs[2 * m], r = pairs[2 * m + 1];
+    rows[k] = (int)(ts.offsets[q + 1] - ts.offsets[q]) - incr;
+    cols[k] = (int)(ts.offsets[r + 1] - ts.offsets[r]) - incr;
+}
+int launch_pair_geometry_map(const TrackSet &ts, const int32_t *pairs, const int32_t *map, int n, int incr, int32_t *rows,
+                             int32_t *cols, cudaStream_t st) {
+    if (n <= 0) return ACOSS_OK;
+    pair_geometry_map_kernel<<<(n + 255) / 256, 256, 0, st>>>(ts, pairs, map, n, incr, rows, cols);
+    CUDA_TRY(cudaGetLastError());
+    return ACOSS_OK;
+}
+__global__ void scatter_scores_kernel(const float *__restrict__ src, const int32_t *__restrict__ map, int n, float *__restrict__ dst) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && map[k] >= 0) dst[map[k]] = src[k];
+}
+int launch_scatter_scores(const float *src, const int32_t *map, int n, float *dst, cudaStream_t st) {
+    if (n <= 0) return ACOSS_OK;
+    scatter_scores_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, map, n, dst);
+    CUDA_TRY(cudaGetLastError());
+    return ACOSS_OK;
+}
+
 // Smith-Waterman over a CRP the pair pipeline emitted (BASELINE.json configs[1]: "Smith-Waterman on the same
 // binary CRPs"): smith_waterman_constrained never reads the last row / column of its input
 // (alignment_tools.py:36-39: B[i-1][j-1], i < M, j < N), so the DP matrix is (rows - 1) x (cols - 1) and the bit

@@ -108,8 +108,11 @@ int acoss_get_tracks(acoss_ctx *ctx, float *frames_out, int64_t total_frames);
  * Ds[key][i][j].  Host buffers; H2D of the pair list and D2H of the scores happen inside. */
 int acoss_score_pairs(acoss_ctx *ctx, const int32_t *pairs, int64_t n_pairs, const acoss_params *p,
                       float *scores);
-/* Same with DEVICE buffers (pairs and scores in HBM), asynchronous on the context's stream;
- * acoss_sync() waits for it.  Used for device-resident timing and for NCCL hand-off. */
+/* Same with DEVICE buffers (pairs and scores in HBM), asynchronous on the context's stream: the call enqueues all
+ * its work and returns without a host synchronisation; acoss_sync() waits for it.  Pairs the fast CRP path flags
+ * (a consistency check failed) are re-scored by the exact path inside the same enqueued work, up to 4 x 16 of them
+ * per call; if a call flags more, acoss_sync() scores the remainder before it returns, so scores_dev is complete
+ * after acoss_sync() in every case.  Used for device-resident timing and for NCCL hand-off. */
 int acoss_score_pairs_device(acoss_ctx *ctx, const int32_t *pairs_dev, int64_t n_pairs,
                              const acoss_params *p, float *scores_dev);
 int acoss_sync(acoss_ctx *ctx);

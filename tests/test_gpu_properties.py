@@ -137,3 +137,36 @@ def test_nan_distance_is_reported(eng):
     with pytest.raises(AcossError) as ei:
         eng.score_pairs([(0, 1)])
     assert ei.value.code == E_NAN
+
+
+def test_many_flagged_pairs_deferred_fallback(eng):
+    """Pairs the fast path flags (here: tracks made of long runs of identical frames, whose rows hold hundreds of
+    tied distances, more than a candidate list takes) are re-scored by the exact path without a host
+    synchronisation inside the call: the first 4 x 16 inside the call's own stream work, the rest inside
+    acoss_sync().  More than 64 of them in one batch exercises both, mixed with ordinary pairs."""
+    from oracle import serra09_c as oc
+    rng = np.random.default_rng(77)
+    tracks = [hp(rng, int(n)) for n in rng.integers(60, 260, size=40)]
+    nt = 14
+    for k in range(nt):                                      # runs of 40 identical frames
+        tracks.append(np.repeat(hp(rng, 5 + k % 3), 40, axis=0))
+    frames, offs = _set(eng, tracks)
+    n = len(tracks)
+    ti, tj = np.triu_indices(nt, k=1)
+    tied = np.stack([40 + ti, 40 + tj], 1)                  # 91 pairs of tie-heavy tracks
+    other = np.stack([rng.integers(0, n, 150), rng.integers(0, n, 150)], 1)
+    pairs = np.concatenate([tied, other]).astype(np.int32)
+    pairs = pairs[rng.permutation(len(pairs))]
+    got = eng.score_pairs(pairs)
+    st = eng.last_stats()
+    assert st["fallback_pairs"] > 64, st                      # both the in-call rounds and the remainder ran
+    want = oc.pairs(frames, offs, pairs, nthreads=8)
+    assert np.array_equal(got, want)
+    # the same through the asynchronous device entry point
+    import torch
+    dp = torch.from_numpy(pairs).cuda()
+    ds = torch.zeros(len(pairs), dtype=torch.float32, device="cuda")
+    eng.score_pairs_device(dp.data_ptr(), len(pairs), ds.data_ptr())
+    eng.sync()
+    assert np.array_equal(ds.cpu().numpy(), want)
+    assert eng.last_stats()["fallback_pairs"] == st["fallback_pairs"]
