@@ -73,8 +73,7 @@ class CoverAlgorithm(object):
             self.filepaths = create_dataset_filepaths(dataset_csv, root_audio_dir=datapath, file_format=".h5")
         self.cliques = {}
         self.N = len(self.filepaths)
-        if not os.path.exists(cachedir):
-            os.mkdir(cachedir)
+        os.makedirs(cachedir, exist_ok=True)                  # (several ranks of one box may construct at once)
         self.Ds = {}
         for s in similarity_types:
             self.Ds[s] = np.memmap("%s_%s_dmat" % (self.get_cacheprefix(), s), shape=(self.N, self.N),

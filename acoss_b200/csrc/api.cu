@@ -170,7 +170,8 @@ int acoss_create(acoss_ctx **out, int device) {
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
+    // sm_100a code is architecture-specific: it does not run on any other compute capability, newer ones included
+    if (prop.major != 10 || prop.minor != 0) {
         acoss_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
         return ACOSS_E_CUDA;
     }
@@ -770,7 +771,8 @@ int acoss_knn_sw(acoss_ctx *c, const double *csms, const int64_t *offsets, const
     for (int64_t k = 0; k < n; ++k) {
         const int M = shapes[2 * k], N = shapes[2 * k + 1];
         if (M <= 0 || N <= 0 || M > 65535 || N > (1 << 20)) { acoss_set_error("knn_sw: bad shape"); return ACOSS_E_INVALID; }
-        if (nn[k] > N) { acoss_set_error("knn_sw: nn > columns (np.argpartition would raise)"); return ACOSS_E_INVALID; }
+        // np.argpartition(D, NNeighbs, 1) needs kth < N (cross_recurrence.py:156): a count equal to the column count raises
+        if (nn[k] >= N) { acoss_set_error("knn_sw: nn >= columns (np.argpartition raises: kth out of bounds)"); return ACOSS_E_INVALID; }
         max_r = std::max(max_r, M); max_c = std::max(max_c, N);
         total = std::max<int64_t>(total, offsets[k] + (int64_t)M * N);
         out_off[k] = out_total;
@@ -981,7 +983,12 @@ static int ef_check_pairs(acoss_ctx *c, const int32_t *pairs, int64_t n, double 
         const int M = (int)(c->ef_hoff[q + 1] - c->ef_hoff[q]), N = (int)(c->ef_hoff[r + 1] - c->ef_hoff[r]);
         // np.partition(CSM, K, axis) raises ValueError when K is not a valid index (similarity_fusion.py:48-51)
         if (K >= M || K >= N) { acoss_set_error("pair %lld: K = %d needs more than K blocks per track (%d x %d); the reference raises ValueError", (long long)k, K, M, N); return ACOSS_E_INVALID; }
-        if (kappa >= 1.0 && (int)kappa > N) { acoss_set_error("pair %lld: kappa = %d neighbours > %d columns (np.argpartition would raise)", (long long)k, (int)kappa, N); return ACOSS_E_INVALID; }
+        // csm_to_binary (cross_recurrence.py:151-156): NNeighbs = kappa (a count) or int(round(kappa * N)); argpartition
+        // needs kth < N, so a neighbour count equal to the column count raises in the reference
+        {
+            const int nnk = (kappa >= 1.0) ? (int)kappa : (int)nearbyint(kappa * (double)N);
+            if (kappa > 0.0 && nnk >= N) { acoss_set_error("pair %lld: %d neighbours >= %d columns (np.argpartition raises: kth out of bounds)", (long long)k, nnk, N); return ACOSS_E_INVALID; }
+        }
         mr = std::max(mr, M); mc = std::max(mc, N);
         cl += (int64_t)M * N;
     }

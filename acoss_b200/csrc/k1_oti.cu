@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) oti_kernel(TrackSet ts, const int32_t *__
 __global__ void __launch_bounds__(256) frame_stats_kernel(const float *__restrict__ frames, int64_t total_frames,
                                                           float *__restrict__ stats2) {
     float mx = 0.f, mn = 0.f;
+    bool bad = false;                                         // NaN / Inf features: fmaxf / fminf would drop them silently
     for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total_frames; f += (int64_t)gridDim.x * blockDim.x) {
         float n2 = 0.f;
 #pragma unroll
@@ -83,8 +84,10 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const float *__restric
             n2 = fmaf(v, v, n2);
             mn = fminf(mn, v);
         }
+        bad |= !(n2 <= 3.0e38f);
         mx = fmaxf(mx, n2);
     }
+    if (__any_sync(0xffffffffu, bad)) mx = __int_as_float(0x7f800000);   // +inf => no fixed point => exact path (flags the NaN)
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));

@@ -264,6 +264,7 @@ __device__ __forceinline__ void ef_cp_async8(void *smem, const void *g) {
 }
 
 // 16 k of one 64 x 64 tile for one thread: acc[i][j] += A[row_i][k] * B[col_j][k], k ascending
+#ifdef ACOSS_EF_GENERATIONS   // superseded generation 2 (DFMA 8x8, cp.async): compiled only for tools/ef_cmp_generations.py
 template <bool FULL>
 __device__ __forceinline__ void ef_tile_fma(const double *Ap, const double *Bp, int jmax, double (&acc)[8][8]) {
 #pragma unroll
@@ -379,6 +380,7 @@ __global__ void __launch_bounds__(64) ef_csm2_kernel(const double *__restrict__ 
     }
 }
 
+#endif  // ACOSS_EF_GENERATIONS
 // ---------------------------------------------------------------------------------------------
 // CSM, third generation: the float64 tensor path (DMMA, mma.sync.m8n8k4.f64 — tcgen05 has no float64
 // kind; on sm_100a the legacy warp-level MMA is the only float64 tensor instruction).  ncu on the second
@@ -529,12 +531,16 @@ __global__ void __launch_bounds__(128) ef_csm3_kernel(const double *__restrict__
 }
 
 static int ef_csm_generation() {
+#ifdef ACOSS_EF_GENERATIONS
     static int gen = -1;
     if (gen < 0) {
         const char *e = getenv("ACOSS_EF_CSM");               // 1 / 2 select the DFMA kernels (A/B timing)
         gen = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3;
     }
     return gen;
+#else
+    return 3;                                                 // the DMMA kernel; ef_csm_kernel only for chroma blocks wider than EF2_MAXDP
+#endif
 }
 
 int launch_ef_csm(int mode, const double *feat, int dp, int d, const double *sq, const int64_t *offsets,
@@ -557,12 +563,14 @@ int launch_ef_csm(int mode, const double *feat, int dp, int d, const double *sq,
         CUDA_TRY(cudaGetLastError());
         return ACOSS_OK;
     }
+#ifdef ACOSS_EF_GENERATIONS
     if (ef_csm_generation() >= 2 && (mode == 0 || dp <= EF2_MAXDP)) {
         if (mode == 0) ef_csm2_kernel<0><<<grid, 64, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
         else ef_csm2_kernel<1><<<grid, 64, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
         CUDA_TRY(cudaGetLastError());
         return ACOSS_OK;
     }
+#endif
     if (mode == 0) ef_csm_kernel<0><<<grid, 128, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
     else ef_csm_kernel<1><<<grid, 128, 0, st>>>(feat, dp, d, sq, offsets, pairs, oti, csm, slot_elems, tiles_n);
     CUDA_TRY(cudaGetLastError());

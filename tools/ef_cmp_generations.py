@@ -1,5 +1,7 @@
 """Dump the float64 matrices of one pair with one generation of the CSM kernel (ACOSS_EF_CSM=1|2|3) to a file,
-or compare two such files bit for bit."""
+or compare two such files bit for bit.  The superseded generations are compiled only into a library built with
+ACOSS_NVCC_EXTRA=-DACOSS_EF_GENERATIONS (python acoss_b200/csrc/build.py); the shipped library carries the DMMA kernel and the
+generic DFMA kernel it falls back to for chroma blocks wider than 2048."""
 import sys
 import numpy as np
 sys.path.insert(0, '.')
