@@ -600,7 +600,10 @@ __device__ __forceinline__ void run_sweep(Sweep<RC> &sw, const float *__restrict
         const ulonglong2 x0 = xs[3 * U], x1 = xs[3 * U + 1], x2 = xs[3 * U + 2];
         sw.dot(x0, x1, x2, eb);
         sw.template finish<U>(eb);
-        if (CALL) fn(a, ps[U]);
+        if (CALL) {
+            const PT prm = ps[U];                  // one read of the row's parameters (the callee may store to shared memory)
+            fn(a, prm);
+        }
         ++a;
     };
     // rows 0..8: the diagonal sums fill up; only row 8 produces a window
@@ -1068,7 +1071,8 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet t
     //   uncertain     <=> row zone or column zone or near zero
     // A near-zero cell that is certainly in is emitted as 1 and listed as well: its exact evaluation either
     // confirms a tiny distance or raises the NaN error.
-    run_sweep<RC, int4>(sw, X, rowpack, nrows, &s_stream[warp], lane, [&](int a, const int4 &rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
+    // (rp by value: a reference into the stage buffer would be re-read after every staging store, which may alias it)
+    run_sweep<RC, int4>(sw, X, rowpack, nrows, &s_stream[warp], lane, [&](int a, const int4 rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
         const int xr = rp.x - rp.y, nz = 2 * EPS - rp.y;
         const unsigned rw1 = (unsigned)(rp.z - 1);
         const int i = a - HALO;                               // CRP row
