@@ -12,13 +12,17 @@ all_gather at the end of the timed region.
 
 Output: ONE JSON line on rank 0 (contract in the task statement), with
   value        device-resident throughput (pairs and scores in HBM, CUDA events, max over ranks)
-  e2e          the same metric through the plugin API Serra09.similarity(idxs): host pair list in,
-               scores read back into the host score matrix, every step
-  roofline     dominant kernel stage (K2, CRP construction) against measured HBM bandwidth; the
-               stage is ALU-issue bound by design, so `roofline_alu` reports cell updates against
-               the lane-instruction issue peak as well
+  e2e          the same metric through the product path at every N: all_pairwise_distributed(Serra09) over the
+               WHOLE C3 pair list (strong scaling): host pair tiles in, host score tiles out, NCCL gather of the
+               score slices at N > 1, N x N matrix assembled and symmetrised; rank-0 tail timed separately
+  roofline     dominant kernel (fast_emit_kernel) against measured HBM bandwidth (contract view) and, in
+               `roofline.binding`, against the instruction-issue roofline that binds it; DRAM traffic and
+               lane-instructions per cell come from the committed ncu capture of this build
+               (profiles/k2_constants.json); `roofline_alu` keeps the per-stage / per-kernel breakdown
+  gather_parity (N > 1) every rank re-scores 64 pairs of another rank's shard against the gathered vector
   cpu_baseline the oracle's plain-C port of the reference CPU path (oracle/serra09_c.c), all host
-               threads, on a bounded sample of the same pairs
+               threads, on a bounded sample of the same pairs; `hoisted` = the same with the norms hoisted
+  c4s          (N=1 only, informational) the pipeline at the realistic ~500-frame track length
   earlyfusion  (N=1 only, informational, after the timed region) the EarlyFusion pair scoring on a covers80-shaped
                slice (BASELINE.json configs[1]): its own e2e, tensor roofline of the float64 DMMA kernel and numpy
                oracle sample; `--no-earlyfusion` skips it

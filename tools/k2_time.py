@@ -38,7 +38,7 @@ with Engine(0) as eng:
     ms = {k: v / a.reps for k, v in eng.stage_ms().items()}
     kms = {k: round(v / a.reps, 3) for k, v in eng.kernel_ms().items()}
     st = eng.last_stats()
-    out = dict(tag=a.tag or os.path.basename(LIB_PATH), config=a.config, pairs=len(pairs), pairs_per_s=len(pairs) / dt,
+    out = dict(tag=a.tag or os.path.basename(LIB_PATH), config=a.config, pairs=len(pairs), cells=cells, pairs_per_s=len(pairs) / dt,
                gcups=cells / dt / 1e9, stage_ms=ms, kernel_ms=kms, fallback=st["fallback_pairs"], chunks=st["chunks"],
                dbg=eng.debug_counters())
     if a.check:
