@@ -49,19 +49,68 @@ def gather_scores(local_scores, bounds, rank: int, world: int, device=None):
     return full
 
 
-def all_pairwise_distributed(alg, symmetric=True, score_fn=None):
+def _tile_store(checkpoint_dir, rank, world, n_pairs, tile, bounds):
+    """Per-rank tile files + manifest for resuming an interrupted all-pairs run (the reference can only reload a
+    COMPLETE run: `precomputed=True`, algorithm_template.py:163-166).  Returns (load, save) closures or (None, None)."""
+    if not checkpoint_dir:
+        return None, None
+    import json
+    import os
+    os.makedirs(checkpoint_dir, exist_ok=True)
+    manifest = dict(world=int(world), n_pairs=int(n_pairs), tile=int(tile), bounds=[int(b) for b in bounds])
+    mpath = os.path.join(checkpoint_dir, "manifest_rank%d.json" % rank)
+    valid = False
+    if os.path.exists(mpath):
+        try:
+            with open(mpath) as f:
+                valid = json.load(f) == manifest
+        except Exception:
+            valid = False
+    if not valid:                                           # different job: forget its tiles
+        for fn in os.listdir(checkpoint_dir):
+            if fn.startswith("rank%d_tile" % rank):
+                os.remove(os.path.join(checkpoint_dir, fn))
+        with open(mpath, "w") as f:
+            json.dump(manifest, f)
+
+    def path(t):
+        return os.path.join(checkpoint_dir, "rank%d_tile%06d.npy" % (rank, t))
+
+    def load(t, n_expected):
+        if os.path.exists(path(t)):
+            try:
+                a = np.load(path(t))
+                if a.shape[-1] == n_expected:
+                    return a
+            except Exception:
+                pass
+        return None
+
+    def save(t, a):
+        tmp = path(t) + ".tmp.npy"
+        np.save(tmp, a)
+        os.replace(tmp, path(t))                            # a tile file is either complete or absent
+    return load, save
+
+
+def all_pairwise_distributed(alg, symmetric=True, score_fn=None, fill_on=None, checkpoint_dir=None, timings=None):
     """Distributed `all_pairwise` for a plugin `alg`.  Every rank calls this; on return every rank's
-    `alg.Ds[key]` holds the full (symmetrised) score matrix of every key.
+    `alg.Ds[key]` holds the full (symmetrised) score matrix of every key (`fill_on=r`: only rank r's, the other
+    ranks skip the assembly — what a benchmark run that evaluates on one rank wants).
 
     Serra09-style plugins (one score per pair; `_pair_array`, `load_features`, `Ds`, `N`, `m`, `tau`) are
     balanced by DP cells (n_q - m tau)(n_r - m tau).  Plugins with several scores per pair (EarlyFusion:
     'mfccs', 'ssms', 'chromas', 'early') provide `pair_weights(pairs)` and `score_pairs(pairs) -> float32
     (n_keys, n)` with rows in `alg.Ds` key order; their score rows travel in ONE gather.
-    `score_fn(pairs)` overrides the scoring call (CPU tests)."""
+    `score_fn(pairs)` overrides the scoring call (CPU tests).  The shard is scored in tiles of `alg.tile_pairs`;
+    with `checkpoint_dir` every finished tile is saved per rank and an interrupted run resumes from the tiles it
+    finds (same world size, pair list and tile size).  `timings` (a dict) receives the seconds of each phase."""
+    import time
     import torch
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
+    t0 = time.perf_counter()
     pairs = alg._pair_array(symmetric)
     if hasattr(alg, "pair_weights"):
         cells = np.asarray(alg.pair_weights(pairs), dtype=np.float64)
@@ -70,17 +119,32 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None):
         incr = int(alg.m) * int(alg.tau)
         cells = (lens[pairs[:, 0]] - incr) * (lens[pairs[:, 1]] - incr)
     bounds = shard_bounds(cells, world)
+    del cells
     mine = pairs[bounds[rank]:bounds[rank + 1]]
     keys = list(alg.Ds.keys())
+    tile = int(getattr(alg, "tile_pairs", 1 << 16))
     if score_fn is not None:
-        local = np.asarray(score_fn(mine), dtype=np.float32)
+        score_tile = lambda p: np.asarray(score_fn(p), dtype=np.float32)
     elif hasattr(alg, "score_pairs"):
-        local = np.asarray(alg.score_pairs(mine), dtype=np.float32)
+        score_tile = lambda p: np.asarray(alg.score_pairs(p), dtype=np.float32)
     else:
         eng = alg.engine()
-        tile = getattr(alg, "tile_pairs", 1 << 16)
-        parts = [eng.score_pairs(mine[k:k + tile].astype(np.int32), alg.params()) for k in range(0, len(mine), tile)]
-        local = np.concatenate(parts) if parts else np.zeros(0, np.float32)
+        score_tile = lambda p: eng.score_pairs(p.astype(np.int32), alg.params())
+    load, save = _tile_store(checkpoint_dir, rank, world, len(pairs), tile, bounds)
+    t1 = time.perf_counter()
+    parts, resumed = [], 0
+    for t, k in enumerate(range(0, len(mine), tile)):
+        p = mine[k:k + tile]
+        got = load(t, len(p)) if load else None
+        if got is None:
+            got = score_tile(p)
+            if save:
+                save(t, got)
+        else:
+            resumed += 1
+        parts.append(got)
+    local = np.concatenate(parts, axis=-1) if parts else np.zeros(0, np.float32)
+    t2 = time.perf_counter()
     rows = 1 if local.ndim == 1 else local.shape[0]
     if rows not in (1, len(keys)):
         raise ValueError("score rows (%d) do not match the score types %r" % (rows, keys))
@@ -95,7 +159,15 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None):
     # one gather for all score rows: rank r contributes rows x (bounds[r+1] - bounds[r]) floats, row-major
     flat = np.ascontiguousarray(local.reshape(rows, -1)).ravel()
     full = gather_scores(torch.from_numpy(flat).to(dev), bounds * rows, rank, world)
-    fill_score_matrices(alg, pairs, full, bounds, rows, keys, symmetric, world)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    t3 = time.perf_counter()
+    if fill_on is None or fill_on == rank:
+        fill_score_matrices(alg, pairs, full, bounds, rows, keys, symmetric, world)
+    t4 = time.perf_counter()
+    if timings is not None:
+        timings.update(shard_s=t1 - t0, score_s=t2 - t1, gather_s=t3 - t2, fill_s=t4 - t3, resumed_tiles=resumed,
+                       tiles=len(parts))
     return bounds
 
 

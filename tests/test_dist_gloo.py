@@ -81,6 +81,63 @@ def test_distributed_shared_cache_prefix_is_not_doubled(tmp_path):
         assert np.array_equal(D, want)
 
 
+_CALLS = []
+
+
+def _worker_resume(rank, world, port, tmp, q):
+    """Tile checkpoints: a second run of the same job scores nothing (all tiles resumed), a different job ignores them."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    os.chdir(tmp)
+    import torch.distributed as dist
+    from acoss_b200.distributed import all_pairwise_distributed
+    from acoss_b200.serra09 import Serra09
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    feats = [dict(hpcp=rng.random((int(n), 12)).astype(np.float32), label=str(i // 3))
+             for i, n in enumerate(rng.integers(20, 200, size=17))]
+    calls = []
+
+    def counting(p):
+        calls.append(len(p))
+        return _fake_score(p)
+    out = []
+    for run in range(2):
+        alg = Serra09(None, None, features=feats, downsample_fac=1, shortname="res%d" % rank, cachedir="cacheres%d" % rank,
+                      tile_pairs=16)
+        tm = {}
+        all_pairwise_distributed(alg, symmetric=True, score_fn=counting, checkpoint_dir="ckpt", timings=tm)
+        out.append((np.array(alg.Ds["main"]), tm["resumed_tiles"], tm["tiles"], sum(calls)))
+        calls.clear()
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_distributed_tile_resume(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_resume, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 17
+    i, j = np.triu_indices(n, k=1)
+    want = np.zeros((n, n), np.float32)
+    want[i, j] = _fake_score(np.stack([i, j], 1))
+    want = want + want.T
+    for rank, out in res:
+        (D1, res1, tiles1, scored1), (D2, res2, tiles2, scored2) = out
+        assert np.array_equal(D1, want) and np.array_equal(D2, want)
+        assert res1 == 0 and scored1 > 0 and tiles1 >= 4        # first run scores every tile
+        assert res2 == tiles2 == tiles1 and scored2 == 0         # second run resumes all of them
+
+
 def _fake_score4(pairs):
     p = np.asarray(pairs, dtype=np.int64)
     base = ((p[:, 0] * 37 + p[:, 1] * 11) % 500).astype(np.float32)
