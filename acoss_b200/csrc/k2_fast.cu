@@ -962,7 +962,7 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet t
                                                              int64_t crp_words) {
     using SW = Sweep<RC>;
     static_assert(RC == 4 && WPC == 4 && EMIT_CW * 32 == WPC * SW::OUTW, "a CTA must own whole CRP words");
-    __shared__ uint32_t s_tile[2][EMIT_ROWS][EMIT_TW];        // [buffer][row][word]
+    __shared__ uint32_t s_tile[2][EMIT_ROWS][EMIT_TW + 1];    // [buffer][row][word] (+1: the last strip's empty spill word)
     __shared__ uint2 s_stage[WPC][EMIT_STAGE][32];            // [warp][entry][lane]: lane-private columns, conflict-free
     __shared__ StreamBuf<int4> s_stream[WPC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -986,7 +986,7 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet t
         }
         return;
     }
-    for (int e = threadIdx.x; e < 2 * EMIT_ROWS * EMIT_TW; e += blockDim.x) (&s_tile[0][0][0])[e] = 0u;
+    for (int e = threadIdx.x; e < 2 * EMIT_ROWS * (EMIT_TW + 1); e += blockDim.x) (&s_tile[0][0][0])[e] = 0u;
     __syncthreads();
     if (warp >= nact) return;
     const int nthr = 32 * nact;
@@ -1031,8 +1031,9 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet t
         const unsigned wi = transpose_nibbles(accI, selA, selB, rotC, mskC);
         accI = 0u;
         uint32_t *ti = &s_tile[blk & 1][grow][tw0];
-        atomicOr(ti, wi << toff);
-        if (toff) atomicOr(ti + 1, wi >> (32 - toff));
+        const unsigned long long w2 = (unsigned long long)wi << toff;      // branch-free: the word and its spill into the next
+        atomicOr(ti, (unsigned)w2);
+        atomicOr(ti + 1, (unsigned)(w2 >> 32));
         // staged uncertain cells -> the pair's pool: exclusive prefix of the lanes' counts, one atomic per warp
         if (__any_sync(0xffffffffu, ns != 0u)) {
             const unsigned cnt = ns;
@@ -1045,6 +1046,7 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet t
             unsigned base = 0u;
             if (lane == 31) base = atomicAdd(pool_ctr, incl);
             base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+#pragma unroll 1
             for (unsigned e = 0; e < cnt; ++e)
                 if (base + e < pool_cap) pool[base + e] = stage[e * 32];
             ns = 0u;
