@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
 // These samples only steer the histogram brackets (select kernel below); exactness never depends
 // on them.
 // ------------------------------------------------------------------------------------------------
-constexpr int SKD = 4;              // diagonals per warp task
+constexpr int SKD = 16;             // diagonals per warp task
 constexpr int SPOS = 32 - HALO;     // window sums one warp pass produces per diagonal (24)
 
 __global__ void __launch_bounds__(128) fast_sample_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
@@ -1221,7 +1221,7 @@ struct WinCell {                    // one window cell to evaluate exactly
 };
 
 // rank: 8 lanes per line, 32 lines per CTA, no CTA-wide synchronisation
-__global__ void __launch_bounds__(256) fast_rank_kernel(int n, FastLayout L, char *__restrict__ scratch) {
+__global__ void __launch_bounds__(256) fast_rank_kernel(int n, FastLayout L, char *__restrict__ scratch, uint32_t *__restrict__ dbg) {
     __shared__ int s_z[32][CAND_CAP];
     __shared__ int s_zsel[32][2];
     __shared__ int s_wn[32][2];
@@ -1248,6 +1248,12 @@ __global__ void __launch_bounds__(256) fast_rank_kernel(int n, FastLayout L, cha
         cnt = (int)min(c, (unsigned)CAND_CAP);
     }
     if (sub == 0) { s_wn[grp][0] = 0; s_wn[grp][1] = 0; s_zsel[grp][0] = 0; s_zsel[grp][1] = 0; }
+#ifdef K2_DEBUG_CNT
+    if (sub == 0 && live) {                                   // candidate-count statistics: lines, sum, sum of squares / 64, max, > 64
+        atomicAdd(&dbg[26], 1u); atomicAdd(&dbg[27], (unsigned)cnt); atomicAdd(&dbg[28], (unsigned)(cnt * cnt) >> 6);
+        atomicMax(&dbg[29], (unsigned)cnt); if (cnt > 64) atomicAdd(&dbg[30], 1u);
+    }
+#endif
     for (int p = sub; p < cnt; p += 8) {
         s_z[grp][p] = candz[p];
         nbelow += cand[p] >> 15;
@@ -1587,7 +1593,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     CUDA_TRY(cudaGetLastError());
     te(K2K_SCATTER);
     tb(K2K_THR);
-    fast_rank_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(n, L, base);
+    fast_rank_kernel<<<dim3((lines + 31) / 32, n), 256, 0, st>>>(n, L, base, dbg);
     te(K2K_THR);
     tb(K2K_EXACT);
     fast_exact_kernel<<<dim3((WFLAT_PER_LINE * lines + 255) / 256, n), 256, 0, st>>>(ts, pairs, first, n, L, base, status, dbg);
