@@ -30,8 +30,9 @@ out = {"git": subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_ou
        "source": note, "report": os.path.relpath(rep), "pairs_per_launch": pairs, "cells_per_launch": cells}
 for r in data:
     name = r[idx["Kernel Name"]]
-    key = "emit" if "fast_emit_kernel" in name else "hist_col" if "fast_hist_kernel<(int)4, (int)0>" in name else \
-          "hist_row" if "fast_hist_kernel<(int)4, (int)1>" in name else None
+    import re
+    mh = re.search(r"fast_hist_kernel<[^,>]*4[^,>]*,\s*[^,>]*([01])\)?>", name)
+    key = "emit" if "fast_emit_kernel" in name else ("hist_col" if mh.group(1) == "0" else "hist_row") if mh else None
     if key is None or key in out:
         continue
     winst = val(r, "smsp__inst_executed.sum")
