@@ -39,7 +39,7 @@ struct acoss_ctx {
     int32_t n_tracks = 0;
     int32_t max_frames = 0, min_frames = 0;
     int64_t total_frames = 0;
-    int32_t fx_exp = -1000, nonneg = 0;
+    int32_t fx_exp = -1000, nonneg = 0, q_exp = -1;
     int64_t ws_limit = (int64_t)24 << 30;
     // grow-only scratch
     Buf pairs, scores, oti, status, crp, rows, cols, thr_q, thr_r, rrot, aa, bb, D, halo, misc, fast, fbmap, dbg, glive;
@@ -261,8 +261,8 @@ static int finish_tracks(acoss_ctx *c, const int64_t *offsets, int32_t n_tracks,
     // feature range for the fast path's fixed point
     TRY(ensure(c->misc, 256));
     TRY(launch_frame_stats(c->d_frames, total, (float *)c->misc.p, c->stream));
-    float st2[2] = {0.f, 0.f};
-    CUDA_TRY(cudaMemcpyAsync(st2, c->misc.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    float st2[3] = {0.f, 0.f, 0.f};
+    CUDA_TRY(cudaMemcpyAsync(st2, c->misc.p, 12, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->nonneg = (st2[1] >= 0.f) ? 1 : 0;
     c->fx_exp = -1000;
@@ -272,6 +272,14 @@ static int finish_tracks(acoss_ctx *c, const int64_t *offsets, int32_t n_tracks,
         c->fx_exp = e;
     }
     if (((uintptr_t)c->d_frames & 15) != 0) c->fx_exp = -1000;   // vector loads need 16 B alignment
+    // tensor sweeps: 24-bit quantisation x_q = rint(x * 2^q_exp) < 2^24 of the non-negative features
+    c->q_exp = -1;
+    if (c->fx_exp > -100 && c->nonneg && st2[2] > 0.f) {
+        int e = 0;
+        frexp((double)st2[2] * 1.000001, &e);        // max feature < 2^e / 1.000001  =>  rint(x * 2^(24 - e)) <= 2^24 - 2
+        const int qe = 24 - e, e0 = 56 - 2 * qe - c->fx_exp;   // limb-product weights in fixed-point units: 2^e0, 2^(e0 - 8), 2^(e0 - 16)
+        if (e0 >= 0 && e0 <= 8) c->q_exp = qe;
+    }
     return ACOSS_OK;
 }
 
@@ -337,7 +345,7 @@ static TrackSet track_set(const acoss_ctx *c) {
     TrackSet ts;
     ts.frames = c->d_frames; ts.offsets = c->d_offsets; ts.gchroma = c->d_gchroma;
     ts.n_tracks = c->n_tracks; ts.max_frames = c->max_frames;
-    ts.fx_exp = c->fx_exp; ts.nonneg = c->nonneg;
+    ts.fx_exp = c->fx_exp; ts.nonneg = c->nonneg; ts.q_exp = c->q_exp;
     return ts;
 }
 

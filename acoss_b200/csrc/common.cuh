@@ -33,6 +33,7 @@ struct TrackSet {
     int32_t max_frames;
     int32_t fx_exp;           // fast path fixed point: 2 * <frame, frame> < 2^fx_exp for every frame pair
     int32_t nonneg;           // 1 when every feature value is >= 0 (HPCP); the fast path requires it
+    int32_t q_exp;            // tensor sweeps: features are quantised as rint(x * 2^q_exp) < 2^24 (three byte limbs); < 0: unavailable
 };
 
 // Per-pair status bits written by the kernels

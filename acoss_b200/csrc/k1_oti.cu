@@ -71,10 +71,10 @@ __global__ void __launch_bounds__(256) oti_kernel(TrackSet ts, const int32_t *__
     if (live && lane == 0) oti_out[sub] = apply ? (best_s == 0x7fffffff ? 0 : best_s) : 0;
 }
 
-// max squared frame norm (as float bits: non-negative floats order like ints) and min feature value
+// max squared frame norm and max feature value (as float bits: non-negative floats order like ints), min feature value
 __global__ void __launch_bounds__(256) frame_stats_kernel(const float *__restrict__ frames, int64_t total_frames,
                                                           float *__restrict__ stats2) {
-    float mx = 0.f, mn = 0.f;
+    float mx = 0.f, mn = 0.f, mc = 0.f;
     bool bad = false;                                         // NaN / Inf features: fmaxf / fminf would drop them silently
     for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total_frames; f += (int64_t)gridDim.x * blockDim.x) {
         float n2 = 0.f;
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const float *__restric
             const float v = frames[f * NBINS + b];
             n2 = fmaf(v, v, n2);
             mn = fminf(mn, v);
+            mc = fmaxf(mc, v);
         }
         bad |= !(n2 <= 3.0e38f);
         mx = fmaxf(mx, n2);
@@ -92,15 +93,17 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const float *__restric
     for (int o = 16; o >= 1; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, o));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMax((int *)&stats2[0], __float_as_int(mx));
         if (mn < 0.f) atomicExch((int *)&stats2[1], __float_as_int(-1.f));
+        atomicMax((int *)&stats2[2], __float_as_int(mc));
     }
 }
 
 int launch_frame_stats(const float *frames, int64_t total_frames, float *stats2, cudaStream_t st) {
-    CUDA_TRY(cudaMemsetAsync(stats2, 0, 8, st));
+    CUDA_TRY(cudaMemsetAsync(stats2, 0, 12, st));
     if (total_frames <= 0) return ACOSS_OK;
     frame_stats_kernel<<<148 * 4, 256, 0, st>>>(frames, total_frames, stats2);
     CUDA_TRY(cudaGetLastError());

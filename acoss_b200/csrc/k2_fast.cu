@@ -35,16 +35,31 @@ constexpr int M9 = 9;               // frameStackSize handled by this path
 constexpr int HALO = M9 - 1;        // owned columns a strip recomputes (8)
 constexpr int NBIN = 64;            // histogram bins per level (+ one underflow and one overflow row)
 constexpr int SBIN = 256;           // bins of the per-line sample histogram (select kernel)
-constexpr int EPS = 128;            // bound on |z - exact item| in fixed-point units
+#ifndef K2_EPS
+#define K2_EPS 128
+#endif
+constexpr int EPS = K2_EPS;            // bound on |z - exact item| in fixed-point units
 constexpr int CAND_CAP = 128;       // candidates per row / column
 constexpr int BRACKET_TARGET = 96;  // a bracket holding more cells than this is split by another histogram level
 constexpr int WPC = 4;              // warps per CTA in the sweep kernels
+constexpr int TC_N = 64;            // streamed windows per tensor-sweep block (MMA N)
+constexpr int TC_PAD = 2 * TC_N;    // padding of per-window arrays and byte planes read in whole blocks
+constexpr int TC_HUGE = 0x20000000; // norm of a padding window: its items land above every bracket
 constexpr int RCV = 4;              // owned frames per lane (register columns) in the sweep kernels
 #ifndef K2_FFMA2
 #define K2_FFMA2 1                  // 1: packed fma.rn.f32x2 dot products (FFMA2); 0: the same chains as scalar FFMA
 #endif
 #ifndef K2_SPLIT
 #define K2_SPLIT 1                  // FMA chains per (even, odd) half of a dot product: 1 = six steps each, 2 = two chains of three
+#endif
+#ifndef K2_HRC
+#define K2_HRC 4                    // register columns per lane of the histogram sweeps
+#endif
+#ifndef K2_HMINB
+#define K2_HMINB K2_MINB            // CTAs per SM the histogram sweeps are compiled for
+#endif
+#ifndef K2_TC
+#define K2_TC 0                     // 1: histogram / emit sweeps and the sparse level on the tensor cores (k2_tc.inl)
 #endif
 #ifndef K2_MINB
 #define K2_MINB 3                   // CTAs per SM the sweep kernels are compiled for (register cap 168 at 3, 255 at 2)
@@ -64,8 +79,9 @@ struct FastLayout {
     size_t slot_bytes;
     size_t off_hdr, off_rrot, off_aaf, off_bbf, off_aai, off_bbi, off_lo, off_w, off_cb, off_sh, off_cnt,
         off_cand, off_candz, off_zin, off_zout, off_rowpack, off_pool, off_pcnt, off_samp_r, off_samp_c,
-        off_lsel, off_wlist, off_wcnt, off_win;
+        off_lsel, off_wlist, off_wcnt, off_win, off_qpl, off_rpl;
     int max_rows, max_cols, max_frames, lines, pool_cap;
+    int plane_frames;                   // frames per byte plane of the tensor sweeps (zero padded past the track end)
     int slog;                           // log2 of the diagonal sampling stride S
     int nst_r, nst_c;                   // sample slots per row (ceil(max_cols / S)) / per column
 };
@@ -82,8 +98,8 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.off_rrot = take((size_t)(max_frames + 8) * NBINS * 4);
     L.off_aaf = take((size_t)g.max_rows * 4);
     L.off_bbf = take((size_t)g.max_cols * 4);
-    L.off_aai = take((size_t)g.max_rows * 4);
-    L.off_bbi = take((size_t)g.max_cols * 4);
+    L.off_aai = take((size_t)(g.max_rows + TC_PAD) * 4);       // padded: the tensor sweeps read whole row blocks
+    L.off_bbi = take((size_t)(g.max_cols + TC_PAD) * 4);
     L.off_lo = take((size_t)L.lines * 4);
     L.off_w = take((size_t)L.lines * 4);
     L.off_cb = take((size_t)L.lines * 4);
@@ -93,7 +109,7 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.off_candz = take((size_t)L.lines * CAND_CAP * 4);
     L.off_zin = take((size_t)L.lines * 4);
     L.off_zout = take((size_t)L.lines * 4);
-    L.off_rowpack = take((size_t)g.max_rows * 16);
+    L.off_rowpack = take((size_t)(g.max_rows + TC_PAD) * 16);
     // uncertain cells of the emit sweep, 8 bytes each (i | j << 14, fixed-point item).  A line contributes its
     // bracket cells (a few tens whatever its length), so the fraction of uncertain cells falls with the line
     // length: ~7 % at 500 frames, ~1.7 % at 2k.  Capacity: ~100 cells per line, at most an eighth of the matrix
@@ -126,6 +142,9 @@ FastLayout make_layout(const SlotGeom &g, int max_frames) {
     L.off_wlist = take((size_t)L.lines * 4 * 8);                // WinCell list: WFLAT_PER_LINE entries per line
     L.off_wcnt = take(4);
     L.off_win = take((size_t)L.lines * 2 * 8 * 4);              // exact items of the window cells: [line][2][WIN_CAP]
+    L.plane_frames = max_frames + TC_PAD + 16;
+    L.off_qpl = take((size_t)3 * L.plane_frames * 16);          // query byte planes [h, l1, l2][frame][16]
+    L.off_rpl = take((size_t)3 * L.plane_frames * 16);          // rotated reference byte planes
     L.slot_bytes = align_up(o, 256);
     return L;
 }
@@ -188,7 +207,7 @@ __device__ __forceinline__ void load_frame(const float *__restrict__ p, float (&
 __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                         const int32_t *__restrict__ oti, int64_t first,
                                                         FastLayout L, char *__restrict__ scratch, float qperc,
-                                                        int guard, float fx_scale) {
+                                                        int guard, float fx_scale, float q_scale) {
     __shared__ int s_max[2];
     const int slot = blockIdx.x;
     const int64_t k = first + slot;
@@ -202,6 +221,30 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
     for (int idx = threadIdx.x; idx < (nr + 8) * NBINS; idx += blockDim.x) {
         const int f = idx / NBINS, b = idx - f * NBINS;
         rrot[idx] = (f < nr) ? R[f * NBINS + rot_src(b, s)] : 0.f;
+    }
+    // byte planes of the tensor sweeps: x_q = rint(x * 2^q_exp) < 2^24 as limbs h, l1, l2; 16-byte frames (12 bins + 4 zeros),
+    // zero frames past the track end
+    if (q_scale > 0.f) {
+        uint4 *qpl = slot_ptr<uint4>(scratch, L, slot, L.off_qpl), *rpl = slot_ptr<uint4>(scratch, L, slot, L.off_rpl);
+        for (int idx = threadIdx.x; idx < 2 * L.plane_frames; idx += blockDim.x) {
+            const bool isq = idx < L.plane_frames;
+            const int f = isq ? idx : idx - L.plane_frames;
+            const int nf = isq ? nq : nr;
+            uint32_t w[3][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+            if (f < nf) {
+#pragma unroll
+                for (int b = 0; b < NBINS; ++b) {
+                    const float v = isq ? Q[(int64_t)f * NBINS + b] : R[(int64_t)f * NBINS + rot_src(b, s)];
+                    const uint32_t xq = (uint32_t)__float2int_rn(v * q_scale);
+                    w[0][b >> 2] |= ((xq >> 16) & 255u) << (8 * (b & 3));
+                    w[1][b >> 2] |= ((xq >> 8) & 255u) << (8 * (b & 3));
+                    w[2][b >> 2] |= (xq & 255u) << (8 * (b & 3));
+                }
+            }
+            uint4 *dst = isq ? qpl : rpl;
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) dst[(size_t)pl * L.plane_frames + f] = make_uint4(w[pl][0], w[pl][1], w[pl][2], 0u);
+        }
     }
     uint32_t *cnt = slot_ptr<uint32_t>(scratch, L, slot, L.off_cnt);
     for (int i = threadIdx.x; i < L.lines; i += blockDim.x) cnt[i] = 0u;
@@ -224,6 +267,8 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
         if (isq) { aaf[i] = v; aai[i] = fx; mxa = max(mxa, fx); }
         else { bbf[i - Mx] = v; bbi[i - Mx] = fx; mxb = max(mxb, fx); }
     }
+    for (int i = Mx + threadIdx.x; i < L.max_rows + TC_PAD; i += blockDim.x) aai[i] = TC_HUGE;   // padding windows
+    for (int i = Nx + threadIdx.x; i < L.max_cols + TC_PAD; i += blockDim.x) bbi[i] = TC_HUGE;
     atomicMax(&s_max[0], mxa);
     atomicMax(&s_max[1], mxb);
     __syncthreads();
@@ -254,7 +299,8 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
         if (quirk2[side]) { lo[i] = 0; w[i] = 0; cb[i] = 0; sh[i] = -1; }
         else { lo[i] = lo1; w[i] = 0; cb[i] = 0; sh[i] = sh1; }
     }
-    for (int i = threadIdx.x; i < Mx; i += blockDim.x) rowpack[i] = make_int4(aai[i], -2 * EPS, 4 * EPS, 0);
+    for (int i = threadIdx.x; i < L.max_rows + TC_PAD; i += blockDim.x)
+        rowpack[i] = make_int4(i < Mx ? aai[i] : TC_HUGE, -2 * EPS, 4 * EPS, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -523,6 +569,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long *b, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
@@ -673,6 +722,11 @@ __device__ __forceinline__ Bracket split_bracket(const uint32_t *hp, int hs, uin
     return r;
 }
 
+constexpr int SPARSE_LEVELS = 3;
+constexpr int DENSE2_MIN_LIVE = 16;  // live lines a strip must hold for the second dense level to sweep it
+
+#include "k2_tc.inl"
+
 // ------------------------------------------------------------------------------------------------
 // histogram sweep.  ORIENT = 0: owned = reference columns (column thresholds), streamed = query.
 //                   ORIENT = 1: owned = query rows (row thresholds), streamed = rotated reference.
@@ -683,7 +737,7 @@ __device__ __forceinline__ Bracket split_bracket(const uint32_t *hp, int hs, uin
 // and the next level splits it).
 // ------------------------------------------------------------------------------------------------
 template <int RC, int ORIENT>
-__global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
+__global__ void __launch_bounds__(32 * WPC, K2_HMINB) fast_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs,
                                                              int64_t first, int n, FastLayout L,
                                                              char *__restrict__ scratch, int strips_max, float magic,
                                                              uint32_t *__restrict__ status, uint32_t *__restrict__ dbg,
@@ -812,8 +866,6 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_hist_kernel(TrackSet t
 // completes per step.  The quantised dot products are the same FMA chains as in the sweeps, so the items
 // are identical.  A warp repeats the sweep until all its lines are done (at most SPARSE_LEVELS times).
 // ------------------------------------------------------------------------------------------------
-constexpr int SPARSE_LEVELS = 3;
-constexpr int DENSE2_MIN_LIVE = 16;  // live lines a strip must hold for the second dense level to sweep it
 
 template <int U>
 __device__ __forceinline__ void sparse_step(const float (&y)[M9][NBINS], int (&acc)[M9], const float (&x)[NBINS], float magic) {
@@ -1495,7 +1547,7 @@ __global__ void collect_fallback_kernel(const uint32_t *__restrict__ status, int
 // host side
 // ------------------------------------------------------------------------------------------------
 bool k2_fast_supported(const acoss_params &p, const SlotGeom &g, const TrackSet &ts) {
-    return p.m == M9 && p.tau == 1 && ts.fx_exp > -100 && ts.nonneg && g.max_rows < 16000 && g.max_cols < 16000 &&
+    return p.m == M9 && p.tau == 1 && ts.fx_exp > -100 && ts.nonneg && (!K2_TC || ts.q_exp >= 0) && g.max_rows < 16000 && g.max_cols < 16000 &&
            g.max_rows >= 2 && g.max_cols >= 2;
 }
 
@@ -1519,24 +1571,27 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     auto tb = [&](int id) { if (timer) timer->begin(id); };
     auto te = [&](int id) { if (timer) timer->end(id); };
     tb(K2K_PREP);
-    fast_prep_kernel<<<n, 256, 0, st>>>(ts, pairs, oti, first, L, base, qperc, p.integer_guard, fx_scale);
+    const float q_scale = ts.q_exp >= 0 ? ldexpf(1.f, ts.q_exp) : 0.f;
+    fast_prep_kernel<<<n, 256, 0, st>>>(ts, pairs, oti, first, L, base, qperc, p.integer_guard, fx_scale, q_scale);
     CUDA_TRY(cudaGetLastError());
     te(K2K_PREP);
-    const int outw = Sweep<RC>::OUTW;
-    const int strips_c = (g.max_cols + outw - 1) / outw, strips_r = (g.max_rows + outw - 1) / outw;
-    const size_t smem = (size_t)WPC * (NBIN + 2) * (RC / 2) * 32 * 4;
+    constexpr int HRC = K2_HRC;
+    const int outw = Sweep<RC>::OUTW, houtw = Sweep<HRC>::OUTW;
+    const int strips_c = (g.max_cols + outw - 1) / outw;                  // emit strips
+    const int hstrips_c = (g.max_cols + houtw - 1) / houtw, hstrips_r = (g.max_rows + houtw - 1) / houtw;
+    const size_t smem = (size_t)WPC * (NBIN + 2) * (HRC / 2) * 32 * 4;
     const size_t smem_sel = (size_t)(SBIN / 2) * SEL_THREADS * 4;
     static bool attr_done_dev[64] = {false};                  // function attributes are per device
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     bool &attr_done = attr_done_dev[dev & 63];
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<RC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<HRC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fast_hist_kernel<HRC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(fast_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
         attr_done = true;
     }
-    const unsigned gc = (unsigned)(((int64_t)n * strips_c + WPC - 1) / WPC), gr = (unsigned)(((int64_t)n * strips_r + WPC - 1) / WPC);
+    const unsigned gc = (unsigned)(((int64_t)n * hstrips_c + WPC - 1) / WPC), gr = (unsigned)(((int64_t)n * hstrips_r + WPC - 1) / WPC);
     const int lines = g.max_rows + g.max_cols;
     // first brackets from every S-th diagonal (sampler + per-line selection), then up to three histogram
     // levels per orientation; a level returns immediately for strips whose lines are all done
@@ -1557,17 +1612,59 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     // two dense levels per orientation: the second sweeps only strips that still hold DENSE2_MIN_LIVE or more live
     // lines (short lines start from the whole item range and need it; ordinary strips skip it at once) and hands
     // every line still live to the sparse refinement
+#if K2_TC
+    {
+        // tensor sweeps (k2_tc.inl): one CTA = 128 owned lines; items from tcgen05.mma.kind::i8 over the byte planes
+        const int e0 = 56 - 2 * ts.q_exp - ts.fx_exp;
+        const TcShift sh3 = {e0, 8 - e0, 16 - e0};
+        const int tstrips_c = (g.max_cols + 127) / 128, tstrips_r = (g.max_rows + 127) / 128;
+        // (requested shared memory also keeps a third CTA off the SM: two CTAs hold the 512 TMEM columns)
+        const size_t smem_h = std::max(sizeof(TcSmem) + (size_t)(NBIN + 2) * 128 * 4, (size_t)80 * 1024);
+        const size_t smem_e = std::max(sizeof(TcSmem) + (size_t)8 * TC_STAGE * 32 * 8, (size_t)80 * 1024);
+        static bool tc_attr_done[64] = {false};
+        if (!tc_attr_done[dev & 63]) {
+            CUDA_TRY(cudaFuncSetAttribute(tc_hist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+            CUDA_TRY(cudaFuncSetAttribute(tc_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+            CUDA_TRY(cudaFuncSetAttribute(tc_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+            tc_attr_done[dev & 63] = true;
+        }
+        const unsigned tgc = (unsigned)((int64_t)n * tstrips_c), tgr = (unsigned)((int64_t)n * tstrips_r);
+        tb(K2K_HIST_COL);
+        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg, 1, 0, glive, gcap, nullptr);
+        te(K2K_HIST_COL);
+        tb(K2K_HIST_ROW);
+        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 4, 1, 0, glive, gcap, nullptr);
+        te(K2K_HIST_ROW);
+        tb(K2K_HIST_COL2);
+        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap, nullptr);
+        te(K2K_HIST_COL2);
+        tb(K2K_HIST_ROW2);
+        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap, nullptr);
+        CUDA_TRY(cudaGetLastError());
+        te(K2K_HIST_ROW2);
+        const int64_t warps = ((int64_t)gcap + 31) / 32;
+        tb(K2K_SPARSE);
+        tc_sparse_kernel<<<(unsigned)((warps + WPC - 1) / WPC), 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, sh3, status, dbg + 8, glive, gcap);
+        CUDA_TRY(cudaGetLastError());
+        te(K2K_SPARSE);
+        const int groups = std::max(tstrips_c, (g.words + 3) / 4);
+        tb(K2K_EMIT);
+        tc_emit_kernel<<<(unsigned)((int64_t)n * groups), TC_THREADS, smem_e, st>>>(ts, pairs, first, n, L, base, groups, sh3, crp, g.words, g.crp_words);
+        CUDA_TRY(cudaGetLastError());
+        te(K2K_EMIT);
+    }
+#else
     tb(K2K_HIST_COL);
-    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg, 1, 0, glive, gcap);
+    fast_hist_kernel<HRC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_c, magic, status, dbg, 1, 0, glive, gcap);
     te(K2K_HIST_COL);
     tb(K2K_HIST_ROW);
-    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 4, 1, 0, glive, gcap);
+    fast_hist_kernel<HRC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_r, magic, status, dbg + 4, 1, 0, glive, gcap);
     te(K2K_HIST_ROW);
     tb(K2K_HIST_COL2);
-    fast_hist_kernel<RC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap);
+    fast_hist_kernel<HRC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap);
     te(K2K_HIST_COL2);
     tb(K2K_HIST_ROW2);
-    fast_hist_kernel<RC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, strips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap);
+    fast_hist_kernel<HRC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap);
     CUDA_TRY(cudaGetLastError());
     te(K2K_HIST_ROW2);
     {
@@ -1588,6 +1685,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
         CUDA_TRY(cudaGetLastError());
         te(K2K_EMIT);
     }
+#endif
     tb(K2K_SCATTER);
     fast_scatter_kernel<<<dim3((L.pool_cap + SCAT_CHUNK - 1) / SCAT_CHUNK, n), 256, 0, st>>>(n, L, base, first, status, dbg);
     CUDA_TRY(cudaGetLastError());
