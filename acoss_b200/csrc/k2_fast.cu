@@ -59,7 +59,7 @@ constexpr int RCV = 4;              // owned frames per lane (register columns) 
 #define K2_HMINB K2_MINB            // CTAs per SM the histogram sweeps are compiled for
 #endif
 #ifndef K2_TC
-#define K2_TC 0                     // 1: histogram / emit sweeps and the sparse level on the tensor cores (k2_tc.inl)
+#define K2_TC 1                     // 1: histogram / emit sweeps and the sparse level on the tensor cores (k2_tc.inl)
 #endif
 #ifndef K2_MINB
 #define K2_MINB 3                   // CTAs per SM the sweep kernels are compiled for (register cap 168 at 3, 255 at 2)
@@ -153,6 +153,11 @@ template <typename T>
 __device__ __forceinline__ T *slot_ptr(char *base, const FastLayout &L, int slot, size_t off) {
     return reinterpret_cast<T *>(base + (size_t)slot * L.slot_bytes + off);
 }
+
+// Per-row parameters of the emit sweep: {aa_fix, 4 EPS - rowLo, rowW + 4 EPS, aa_fix - rowLo + 2 EPS}.  With ar = z - (rowLo - 2 EPS):
+//   ar = .w + bb - T,   row zone <=> (unsigned)ar < .z,   near zero (z < 2 EPS) <=> ar < .y,   rowLo - 2 EPS = 2 EPS - .y
+__device__ __forceinline__ int4 pack_row(int aa, int lo, int w) { return make_int4(aa, 4 * EPS - lo, w + 4 * EPS, aa - lo + 2 * EPS); }
+__device__ __forceinline__ int row_lo_e(const int4 &rp) { return 2 * EPS - rp.y; }
 
 // ------------------------------------------------------------------------------------------------
 // Fixed-point frame-level dot product.  2<x, y> is accumulated by TWO fused-multiply-add chains (even and odd
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(256) fast_prep_kernel(TrackSet ts, const int32
         else { lo[i] = lo1; w[i] = 0; cb[i] = 0; sh[i] = sh1; }
     }
     for (int i = threadIdx.x; i < L.max_rows + TC_PAD; i += blockDim.x)
-        rowpack[i] = make_int4(i < Mx ? aai[i] : TC_HUGE, -2 * EPS, 4 * EPS, 0);
+        rowpack[i] = pack_row(i < Mx ? aai[i] : TC_HUGE, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -845,7 +850,7 @@ __global__ void __launch_bounds__(32 * WPC, K2_HMINB) fast_hist_kernel(TrackSet 
         n_left += br.done ? 0 : 1;
         if (ORIENT == 1) {
             int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
-            rowpack[j] = make_int4(yn[j], br.lo - 2 * EPS, br.w + 4 * EPS, 0);
+            rowpack[j] = pack_row(yn[j], br.lo, br.w);
         }
         if (!br.done && final_level) to_sparse(j);            // the sparse level refines it
     }
@@ -966,7 +971,7 @@ __global__ void __launch_bounds__(32 * WPC, 2) fast_sparse_kernel(TrackSet ts, c
             else {
                 lo = br.lo; sh = br.sh;
                 lo_a[j] = br.lo; w_a[j] = br.w; cb_a[j] = br.below; sh_a[j] = br.done ? -1 : br.sh;
-                if (side == 0) slot_ptr<int4>(scratch, L, slot, L.off_rowpack)[j] = make_int4(ynj, br.lo - 2 * EPS, br.w + 4 * EPS, 0);
+                if (side == 0) slot_ptr<int4>(scratch, L, slot, L.off_rowpack)[j] = pack_row(ynj, br.lo, br.w);
                 if (br.done) livel = false;
             }
         }
@@ -1126,8 +1131,8 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet t
     // A near-zero cell that is certainly in is emitted as 1 and listed as well: its exact evaluation either
     // confirms a tiny distance or raises the NaN error.
     // (rp by value: a reference into the stage buffer would be re-read after every staging store, which may alias it)
-    run_sweep<RC, int4>(sw, X, rowpack, nrows, &s_stream[warp], lane, [&](int a, const int4 rp) {   // rp = {aa_fix, rowLo - 2EPS, rowW + 4EPS, -}
-        const int xr = rp.x - rp.y, nz = 2 * EPS - rp.y;
+    run_sweep<RC, int4>(sw, X, rowpack, nrows, &s_stream[warp], lane, [&](int a, const int4 rp) {   // rp = pack_row(..)
+        const int xr = rp.w, nz = rp.y;
         const unsigned rw1 = (unsigned)(rp.z - 1);
         const int i = a - HALO;                               // CRP row
         const unsigned rec0 = (unsigned)i | jcol0;
@@ -1138,7 +1143,7 @@ __global__ void __launch_bounds__(32 * WPC, K2_MINB) fast_emit_kernel(TrackSet t
             const bool unc = ((unsigned)ar <= rw1) || ((unsigned)ac <= cw1[kk]) || (ar < nz);
             accI = __funnelshift_l((unsigned)(ar & ac), accI, 1);   // sign bit -> bit 0, earlier cells move up
             if (unc) {
-                stage[ns * 32] = make_uint2(rec0 + ((unsigned)kk << 14), (unsigned)(ar + rp.y));
+                stage[ns * 32] = make_uint2(rec0 + ((unsigned)kk << 14), (unsigned)ar);
                 ++ns;
             }
         }
@@ -1186,9 +1191,8 @@ __global__ void __launch_bounds__(256) fast_scatter_kernel(int n, FastLayout L, 
             if (e < m) {
                 const uint2 rec = pool[e];
                 const int i = rec.x & 0x3fff, j = (rec.x >> 14) & 0x3fff;
-                const int z = (int)rec.y;
-                const int4 rp = rowpack[i];                   // {aa_fix, rowLo - 2 EPS, rowW + 4 EPS, -}
-                const int ar = z - rp.y, ac = z - (lo_c[j] - 2 * EPS);
+                const int4 rp = rowpack[i];                   // pack_row(..)
+                const int ar = (int)rec.y, z = ar + row_lo_e(rp), ac = z - (lo_c[j] - 2 * EPS);   // the record carries ar = z - (rowLo - 2 EPS)
                 const bool zz = z < 2 * EPS;                  // near-zero item: always evaluated exactly
                 rz[u] = (ar >= 0 && ar < rp.z) || zz;
                 cz[u] = ac >= 0 && ac < w_c[j] + 4 * EPS;
@@ -1509,7 +1513,7 @@ __global__ void __launch_bounds__(256) fast_resolve_bits_kernel(TrackSet ts, con
         const bool zz = z < 2 * EPS;
         if (!isrow) {                                         // also on the row's list? then the row handles it
             const int4 rp = rowpack[i];
-            const int ar = z - rp.y;
+            const int ar = z - row_lo_e(rp);
             if ((ar >= 0 && ar < rp.z) || zz) continue;
         }
         const int lr = i, lc = L.max_rows + j;
@@ -1616,11 +1620,11 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     {
         // tensor sweeps (k2_tc.inl): one CTA = 128 owned lines; items from tcgen05.mma.kind::i8 over the byte planes
         const int e0 = 56 - 2 * ts.q_exp - ts.fx_exp;
-        const TcShift sh3 = {e0, 8 - e0, 16 - e0};
+        const TcShift sh3 = {e0, 8 - e0, 16 - e0, 1u << e0};
         const int tstrips_c = (g.max_cols + 127) / 128, tstrips_r = (g.max_rows + 127) / 128;
-        // (requested shared memory also keeps a third CTA off the SM: two CTAs hold the 512 TMEM columns)
-        const size_t smem_h = std::max(sizeof(TcSmem) + (size_t)(NBIN + 2) * 128 * 4, (size_t)80 * 1024);
-        const size_t smem_e = std::max(sizeof(TcSmem) + (size_t)8 * TC_STAGE * 32 * 8, (size_t)80 * 1024);
+        // (one CTA per SM: it holds all 512 TMEM columns; the requested shared memory keeps a second one off the SM)
+        const size_t smem_h = std::max(sizeof(TcSmem) + (size_t)(NBIN + 2) * 128 * 4, (size_t)120 * 1024);
+        const size_t smem_e = std::max(sizeof(TcSmem) + (size_t)(TC_CONS / 32) * (TC_STAGE * 32 * 8 + 64), (size_t)120 * 1024);
         static bool tc_attr_done[64] = {false};
         if (!tc_attr_done[dev & 63]) {
             CUDA_TRY(cudaFuncSetAttribute(tc_hist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
@@ -1629,17 +1633,18 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
             tc_attr_done[dev & 63] = true;
         }
         const unsigned tgc = (unsigned)((int64_t)n * tstrips_c), tgr = (unsigned)((int64_t)n * tstrips_r);
+        static const int tcdbg = getenv("ACOSS_TC_DBG") ? atoi(getenv("ACOSS_TC_DBG")) : 0;
         tb(K2K_HIST_COL);
-        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg, 1, 0, glive, gcap, nullptr);
+        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg, 1, 0, glive, gcap, tcdbg);
         te(K2K_HIST_COL);
         tb(K2K_HIST_ROW);
-        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 4, 1, 0, glive, gcap, nullptr);
+        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 4, 1, 0, glive, gcap, tcdbg);
         te(K2K_HIST_ROW);
         tb(K2K_HIST_COL2);
-        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap, nullptr);
+        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap, 0);
         te(K2K_HIST_COL2);
         tb(K2K_HIST_ROW2);
-        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap, nullptr);
+        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap, 0);
         CUDA_TRY(cudaGetLastError());
         te(K2K_HIST_ROW2);
         const int64_t warps = ((int64_t)gcap + 31) / 32;
@@ -1661,10 +1666,10 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     fast_hist_kernel<HRC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_r, magic, status, dbg + 4, 1, 0, glive, gcap);
     te(K2K_HIST_ROW);
     tb(K2K_HIST_COL2);
-    fast_hist_kernel<HRC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap);
+    fast_hist_kernel<HRC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap, 0);
     te(K2K_HIST_COL2);
     tb(K2K_HIST_ROW2);
-    fast_hist_kernel<HRC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap);
+    fast_hist_kernel<HRC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap, 0);
     CUDA_TRY(cudaGetLastError());
     te(K2K_HIST_ROW2);
     {

@@ -15,34 +15,45 @@
 //   * consumer threads read their owned window's 64 items from TMEM (tcgen05.ld 32x32b: TMEM lane = owned window,
 //     column = streamed window) and bin / classify them: no dot products, no sliding sums, no shuffles on the
 //     CUDA cores.
-// T = (acc0 << s0) + (acc1 >> s1) + (acc2 >> s2) is 2 <X, Y> in the fixed-point unit of the path (shifts from q_exp and
+// T = (acc0 << s0) + ((acc1 * 256 + acc2) >> s2) is 2 <X, Y> in the fixed-point unit of the path (shifts from q_exp and
 // fx_exp); the sparse level evaluates the same integer formula with dp4a, so every kernel sees identical items.
 // Error budget against the exact item: quantisation 216 x_max 2^-(q_exp+1) * 2, dropped limb products
 // 2 * 108 * 255^2 * 2^(9 - 2 q_exp), two floors: 36 units at HPCP scale, inside EPS.
 
-struct TcShift { int s0, s1, s2; };
+struct TcShift { int s0, s1, s2; unsigned m0; };   // m0 = 2^s0
 
 constexpr int TC_AF = 144;                          // owned frames held per plane (128 windows + 9 taps, rounded)
 constexpr int TC_ALOAD = 137;                       // owned frames loaded per plane
-constexpr int TC_BF = 72;                           // streamed frames per plane and stage (64 windows + 8)
-constexpr int TC_CONS = 256;                        // consumer threads: warp w reads TMEM lanes 32 (w & 3) .., block half w >> 2
-constexpr int TC_THREADS = TC_CONS + 32;            // + one producer warp (TMA, MMA issue, TMEM allocation)
-constexpr int TC_TMEM_COLS = 256;                   // three accumulators of 64 columns (allocation: power of two)
+constexpr int TC_BF = TC_N + 8;                     // streamed frames per plane and stage
+constexpr int TC_BST = 3;                           // streamed-plane stages
+constexpr int TC_PARTS = TC_N / 16;                 // 16-window parts of a block: one consumer warp per (TMEM lane quarter, part)
+constexpr int TC_CONS = 4 * TC_PARTS * 32;          // consumer threads: warp w reads TMEM lanes 32 (w & 3) .., part w >> 2
+constexpr int TC_THREADS = TC_CONS + 96;            // + three producer warps: two MMA issuers (the first allocates TMEM), one TMA loader
+constexpr int TC_TMEM_COLS = 512;                   // two buffers of three accumulators (TC_N columns each) + the owned operand tiles
+constexpr int TC_BUF = 3 * TC_N;                    // columns of one accumulator buffer
+constexpr int TC_ACOL = 2 * TC_BUF;                 // first column of the owned operand: 15 tiles (plane, tap pair) of 8 columns
+static_assert(TC_ACOL + 15 * 8 <= 512 && TC_N % 16 == 0, "accumulators and owned tiles must fit the tensor memory");
 
 struct alignas(128) TcSmem {
     uint8_t a[3][TC_AF][16];                        // owned planes h, l1, l2
-    uint8_t b[2][3][TC_BF][16];                     // streamed planes, two stages
+    uint8_t b[TC_BST][3][TC_BF][16];                // streamed planes
     uint8_t zero[TC_N][16];
-    unsigned long long afull, bfull[2], bfree[2], acc_full, acc_free;
+    unsigned long long afull, aready, bfull[TC_BST], bfree[TC_BST], acc_full[2], acc_free[2];
     uint32_t tmem_base;
 };
+
+// 2 <X, Y> in fixed-point units from the three limb-product accumulators (one floor; the same expression in every kernel)
+__device__ __forceinline__ int tc_item(int v0, int v1, int v2, const TcShift &sh) {
+    const unsigned low = ((unsigned)v1 << 8) + (unsigned)v2;          // < 2^32: v1 <= 2 * 108 * 255^2, v2 <= 3 * 108 * 255^2
+    return (int)((unsigned)v0 * sh.m0 + (low >> sh.s2));      // IMAD + SHF + IMAD: one instruction on the integer ALU pipe
+}
 
 // K-major, no swizzle: ((8, m), 2) : ((16 B, SBO), LBO); version 1 (sm_100)
 __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t lbo_bytes) {
     return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)(128u >> 4) << 32) |
            ((uint64_t)1 << 46);
 }
-// instruction descriptor: s32 accumulators, u8 x u8, both K-major, M = 128, N = 64
+// instruction descriptor: s32 accumulators, u8 x u8, both K-major, M = 128, N = TC_N
 constexpr uint32_t TC_IDESC = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -54,6 +65,22 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
         : "memory");
+}
+// A operand from tensor memory (lane = row, 8 columns = the row's 32 bytes)
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
 }
 __device__ __forceinline__ void tc_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -69,14 +96,18 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// the 30 MMAs of one block: acc0 = h.h, acc1 = h.l1 + l1.h, acc2 = l1.l1 + h.l2 + l2.h  (owned plane, streamed plane)
-__device__ __forceinline__ void tc_issue_block(uint32_t a0, uint32_t b0, uint32_t zero, uint32_t tmem) {
-    constexpr uint32_t PA = TC_AF * 16, PB = TC_BF * 16;
+// the 30 MMAs of one block: acc0 = h.h, acc1 = h.l1 + l1.h, acc2 = l1.l1 + h.l2 + l2.h  (owned plane, streamed plane).
+// The owned operand comes from tensor memory (tile (plane, tap pair) = rows' frames [m + 2 tp | m + 2 tp + 1], written once per
+// CTA by tc_fill_owned): shared memory then only delivers the streamed side (2 KB per MMA instead of 6 KB; the consumers'
+// shared-memory atomics and the MMA's operand fetch otherwise fight for the same 128 B / clk).
+__device__ __forceinline__ void tc_issue_block(uint32_t b0, uint32_t zero, uint32_t tmem, uint32_t acc_col) {
+    constexpr uint32_t PB = TC_BF * 16;
     auto prod = [&](uint32_t pa, uint32_t pb, uint32_t acc, bool first) {
-        const uint32_t sa = a0 + pa * PA, sb = b0 + pb * PB;
+        const uint32_t sb = b0 + pb * PB;
 #pragma unroll
-        for (int t = 0; t < 8; t += 2) tc_mma(tmem + acc * TC_N, tc_desc(sa + 16 * t, 16), tc_desc(sb + 16 * t, 16), !(first && t == 0));
-        tc_mma(tmem + acc * TC_N, tc_desc(sa + 16 * 8, 16), tc_desc(sb + 16 * 8, zero - (sb + 16 * 8)), 1u);   // tap 8 x (tap 8, zeros)
+        for (int tp = 0; tp < 5; ++tp)
+            tc_mma_ts(tmem + acc_col + acc * TC_N, tmem + TC_ACOL + 8 * (pa * 5 + tp),
+                      tc_desc(sb + 32 * tp, tp == 4 ? zero - (sb + 32 * tp) : 16), !(first && tp == 0));   // tap 8 pairs with zeros
     };
     prod(0, 0, 0, true);
     prod(0, 1, 1, true);
@@ -85,37 +116,61 @@ __device__ __forceinline__ void tc_issue_block(uint32_t a0, uint32_t b0, uint32_
     prod(0, 2, 2, false);
     prod(2, 0, 2, false);
 }
+// consumer warps 0..3 (TMEM lane quarters): owned planes (shared memory, landed on afull) -> the 15 operand tiles
+__device__ __forceinline__ void tc_fill_owned(TcSmem *s, uint32_t tmem, int warp, int lane) {
+    mbar_wait(&s->afull, 0);
+    const int m = warp * 32 + lane;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+        for (int tp = 0; tp < 5; ++tp) {
+            const uint4 f0 = *reinterpret_cast<const uint4 *>(&s->a[pl][m + 2 * tp][0]);
+            const uint4 f1 = *reinterpret_cast<const uint4 *>(&s->a[pl][m + 2 * tp + 1][0]);
+            const uint32_t v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            tc_st8(tmem + ((uint32_t)(warp * 32) << 16) + TC_ACOL + 8 * (pl * 5 + tp), v);
+        }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s->aready);
+}
 
-// Producer warp (one elected lane): owned planes once, then per block the streamed planes (double buffered) and the MMAs.
-__device__ __forceinline__ void tc_producer(TcSmem *s, const uint8_t *__restrict__ own, const uint8_t *__restrict__ str,
-                                            size_t plane_bytes, int own_first, int nblocks, uint32_t tmem) {
-    auto load_b = [&](int b) {
-        const int st = b & 1;
+// Producer warps (one elected lane each).  Loader: owned planes once, then the streamed planes of every block (three
+// stages).  Two MMA issuers, one per accumulator buffer (even / odd blocks): while one waits for its buffer or commits, the
+// other keeps the tensor pipe fed (a single issuer spends a third of its time in barrier waits and copy issue).
+__device__ __forceinline__ void tc_loader(TcSmem *s, const uint8_t *__restrict__ own, const uint8_t *__restrict__ str, size_t plane_bytes,
+                                          int own_first, int nblocks) {
+    mbar_expect_tx(&s->afull, 3 * TC_ALOAD * 16);
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) bulk_g2s(&s->a[pl][0][0], own + pl * plane_bytes + (size_t)own_first * 16, TC_ALOAD * 16, &s->afull);
+    for (int b = 0; b < nblocks; ++b) {
+        const int st = b % TC_BST;
+        if (b >= TC_BST) mbar_wait(&s->bfree[st], (uint32_t)((b / TC_BST - 1) & 1));   // the MMAs of block b - 3 have read the stage
         mbar_expect_tx(&s->bfull[st], 3 * TC_BF * 16);
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl)
             bulk_g2s(&s->b[st][pl][0][0], str + pl * plane_bytes + (size_t)b * TC_N * 16, TC_BF * 16, &s->bfull[st]);
-    };
-    mbar_expect_tx(&s->afull, 3 * TC_ALOAD * 16);
-#pragma unroll
-    for (int pl = 0; pl < 3; ++pl) bulk_g2s(&s->a[pl][0][0], own + pl * plane_bytes + (size_t)own_first * 16, TC_ALOAD * 16, &s->afull);
-    load_b(0);
-    if (nblocks > 1) load_b(1);
-    mbar_wait(&s->afull, 0);
-    const uint32_t a0 = smem_u32(&s->a[0][0][0]), zero = smem_u32(&s->zero[0][0]);
-    for (int b = 0; b < nblocks; ++b) {
-        const int st = b & 1;
-        mbar_wait(&s->bfull[st], (uint32_t)((b >> 1) & 1));
-        if (b > 0) mbar_wait(&s->acc_free, (uint32_t)((b - 1) & 1));      // consumers hold block b - 1 in registers
-        tc_fence_after();
-        tc_issue_block(a0, smem_u32(&s->b[st][0][0][0]), zero, tmem);
-        tc_commit(&s->acc_full);
-        tc_commit(&s->bfree[st]);
-        if (b + 2 < nblocks) {
-            mbar_wait(&s->bfree[st], (uint32_t)((b >> 1) & 1));           // the MMAs of block b have read stage st
-            load_b(b + 2);
-        }
     }
+}
+__device__ __forceinline__ void tc_issuer(TcSmem *s, int buf, int nblocks, uint32_t tmem) {
+    mbar_wait(&s->aready, 0);
+    const uint32_t zero = smem_u32(&s->zero[0][0]);
+    for (int b = buf; b < nblocks; b += 2) {
+        const int st = b % TC_BST;
+        mbar_wait(&s->bfull[st], (uint32_t)((b / TC_BST) & 1));
+        if (b >= 2) mbar_wait(&s->acc_free[buf], (uint32_t)(((b >> 1) - 1) & 1));   // consumers hold block b - 2 in registers
+        tc_fence_after();
+        tc_issue_block(smem_u32(&s->b[st][0][0][0]), zero, tmem, buf * TC_BUF);
+        tc_commit(&s->acc_full[buf]);
+        tc_commit(&s->bfree[st]);
+    }
+}
+// role dispatch of the three producer warps (warp index relative to the first producer warp)
+__device__ __forceinline__ void tc_producers(TcSmem *s, int pwarp, int lane, const uint8_t *__restrict__ own, const uint8_t *__restrict__ str,
+                                             size_t plane_bytes, int own_first, int nblocks, uint32_t tmem) {
+    if (lane != 0) return;
+    if (pwarp == 2) tc_loader(s, own, str, plane_bytes, own_first, nblocks);
+    else tc_issuer(s, pwarp, nblocks, tmem);
 }
 
 // Common CTA prologue / epilogue: barriers, zero block, TMEM allocation by the producer warp.
@@ -124,13 +179,12 @@ __device__ __forceinline__ uint32_t tc_begin(TcSmem *s) {
     for (int i = tid; i < TC_N * 16 / 4; i += TC_THREADS) reinterpret_cast<uint32_t *>(&s->zero[0][0])[i] = 0u;
     if (tid == 0) {
         mbar_init(&s->afull, 1);
-        mbar_init(&s->bfull[0], 1); mbar_init(&s->bfull[1], 1);
-        mbar_init(&s->bfree[0], 1); mbar_init(&s->bfree[1], 1);
-        mbar_init(&s->acc_full, 1);
-        mbar_init(&s->acc_free, TC_CONS);
+        mbar_init(&s->aready, 4);
+        for (int i = 0; i < TC_BST; ++i) { mbar_init(&s->bfull[i], 1); mbar_init(&s->bfree[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s->acc_full[i], 1); mbar_init(&s->acc_free[i], TC_CONS / 32); }
         mbar_fence_init();
     }
-    if (tid >= TC_CONS) {
+    if (tid >= TC_CONS && tid < TC_CONS + 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s->tmem_base)), "n"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -143,29 +197,45 @@ __device__ __forceinline__ uint32_t tc_begin(TcSmem *s) {
 __device__ __forceinline__ void tc_end(uint32_t tmem) {
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x >= TC_CONS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+    if (threadIdx.x >= TC_CONS && threadIdx.x < TC_CONS + 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
 }
 
-// Consumer side of one block: fn(chunk_first_window, acc0[16], acc1[16], acc2[16]) for the two 16-window chunks of this warp's
-// half.  The accumulators are released (acc_free) as soon as the last chunk sits in registers.
-template <typename Fn>
-__device__ __forceinline__ void tc_consume_block(TcSmem *s, uint32_t tmem, int b, int warp, Fn &&fn) {
-    mbar_wait(&s->acc_full, (uint32_t)(b & 1));
-    tc_fence_after();
-    const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 32);
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-        int v0[16], v1[16], v2[16];
-        tc_ld16(tbase + ch * 16, v0);
-        tc_ld16(tbase + TC_N + ch * 16, v1);
-        tc_ld16(tbase + 2 * TC_N + ch * 16, v2);
-        tc_ld_wait();
-        if (ch == 1) {
-            tc_fence_before();
-            mbar_arrive(&s->acc_free);
-        }
-        fn(b * TC_N + (warp >> 2) * 32 + ch * 16, v0, v1, v2);
+// mbarrier wait of the consumer warps: polls back off so that twenty waiting warps do not fight the MMA's operand reads for
+// shared-memory bandwidth
+__device__ __forceinline__ void tc_wait_sleep(unsigned long long *b, uint32_t parity) {
+    uint32_t done = 0;
+    for (;;) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(200);
     }
+}
+
+__device__ __forceinline__ void tc_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Consumer side of one block: fn(first_window, acc0[16], acc1[16], acc2[16]) for this warp's 16 windows.  The accumulator
+// buffer is released (acc_free) as soon as the values sit in registers.
+template <typename Fn>
+__device__ __forceinline__ void tc_consume_block(TcSmem *s, uint32_t tmem, int b, int warp, Fn &&fn, int dbgmode = 0) {
+    const int buf = b & 1;
+    tc_wait_sleep(&s->acc_full[buf], (uint32_t)((b >> 1) & 1));
+    tc_fence_after();
+    const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * TC_BUF + (warp >> 2) * 16);
+    int v0[16], v1[16], v2[16];
+    if (dbgmode == 4) {
+        tc_fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&s->acc_free[buf]);
+        return;
+    }
+    tc_ld16(tbase, v0);
+    tc_ld16(tbase + TC_N, v1);
+    tc_ld16(tbase + 2 * TC_N, v2);
+    tc_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&s->acc_free[buf]);       // one arrival per consumer warp
+    fn(b * TC_N + (warp >> 2) * 16, v0, v1, v2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -173,11 +243,10 @@ __device__ __forceinline__ void tc_consume_block(TcSmem *s, uint32_t tmem, int b
 // windows; 1 = owned query rows, streamed reference windows.  One CTA = 128 owned lines of one pair.
 // ------------------------------------------------------------------------------------------------
 template <int ORIENT>
-__global__ void __launch_bounds__(TC_THREADS, 2) tc_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n,
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n,
                                                                 FastLayout L, char *__restrict__ scratch, int strips_max, TcShift sh3,
                                                                 uint32_t *__restrict__ status, uint32_t *__restrict__ dbg, int min_live,
-                                                                int final_level, uint32_t *__restrict__ glive, uint32_t gcap,
-                                                                int32_t *__restrict__ dbgz) {
+                                                                int final_level, uint32_t *__restrict__ glive, uint32_t gcap, int dbgmode) {
     extern __shared__ __align__(128) unsigned char tc_raw[];
     TcSmem *s = reinterpret_cast<TcSmem *>(tc_raw);
     uint32_t *hist = reinterpret_cast<uint32_t *>(tc_raw + sizeof(TcSmem));   // [NBIN + 2][128]
@@ -208,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_hist_kernel(TrackSet ts, con
     const int shf = valid ? shv : 0;
     // bin = ((z - lo) >> sh) + 1 clamped to [0, NBIN + 1]; idle lines land in the overflow bin
     const int ynrel = valid ? yn[j] - lo_a[j] + (1 << shv) : 0x40000000;
-    const bool scan = valid && warp < 4;                     // one thread per line scans (both halves count into one histogram)
+    const bool scan = valid && warp < 4;                     // one thread per line scans (all parts count into one histogram)
     const int n_live_cta = __syncthreads_count(scan);
     if (n_live_cta == 0) return;
     auto to_sparse = [&](int line) {
@@ -220,19 +289,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_hist_kernel(TrackSet ts, con
         if (scan) to_sparse(j);
         return;
     }
+    const long long T0 = clock64();
+    const bool prt = (dbgmode >= 8) && blockIdx.x == 5000;
     for (int i = tid; i < (NBIN + 2) * 128; i += TC_THREADS) hist[i] = 0u;
     const uint32_t tmem = tc_begin(s);
+    const long long T1 = clock64();
     const int nblocks = (Mxs + TC_N - 1) / TC_N;
     if (!cons) {
-        if (lane == 0) {
-            const uint8_t *qpl = slot_ptr<uint8_t>(scratch, L, slot, L.off_qpl), *rpl = slot_ptr<uint8_t>(scratch, L, slot, L.off_rpl);
-            tc_producer(s, ORIENT == 0 ? rpl : qpl, ORIENT == 0 ? qpl : rpl, (size_t)L.plane_frames * 16, cb, nblocks, tmem);
-        }
+        const uint8_t *qpl = slot_ptr<uint8_t>(scratch, L, slot, L.off_qpl), *rpl = slot_ptr<uint8_t>(scratch, L, slot, L.off_rpl);
+        tc_producers(s, warp - TC_CONS / 32, lane, ORIENT == 0 ? rpl : qpl, ORIENT == 0 ? qpl : rpl, (size_t)L.plane_frames * 16, cb, nblocks, tmem);
     } else {
+        if (warp < 4) tc_fill_owned(s, tmem, warp, lane);
         uint32_t *hp = hist + tl;
+        long long Tb1 = 0;
         for (int b = 0; b < nblocks; ++b) {
+            if (b == 1) Tb1 = clock64();
+            if (lane == 0 && b + 1 < nblocks) tc_prefetch_l1(xn + (b + 1) * TC_N + (warp >> 2) * 16);   // next block's 16 norms (64 B)
             tc_consume_block(s, tmem, b, warp, [&](int r0, const int (&v0)[16], const int (&v1)[16], const int (&v2)[16]) {
                 const int4 *xp = reinterpret_cast<const int4 *>(xn + r0);
+                if (dbgmode == 2) { if (v0[0] + v1[3] + v2[7] == 0x12345678) atomicAdd(&hp[0], 1u); return; }
+                if (dbgmode == 3) { int a = 0; for (int g = 0; g < 4; ++g) { const int4 xv = __ldg(xp + g); a += xv.x + xv.y + xv.z + xv.w; } for (int i = 0; i < 16; ++i) a += tc_item(v0[i], v1[i], v2[i], sh3) >> shf; if (a == 0x12345678) atomicAdd(&hp[0], 1u); return; }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const int4 xv = __ldg(xp + g);
@@ -240,16 +316,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_hist_kernel(TrackSet ts, con
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int i = 4 * g + u;
-                        const int T = (v0[i] << sh3.s0) + (v1[i] >> sh3.s1) + (v2[i] >> sh3.s2);
-                        const int zr = xb[u] + ynrel - T;
+                        const int zr = xb[u] + ynrel - tc_item(v0[i], v1[i], v2[i], sh3);
                         const int idx = __vimin_s32_relu(zr >> shf, NBIN + 1);
                         atomicAdd(&hp[idx * 128], 1u);
-                        if (dbgz && slot == 0 && strip == 0 && r0 + i < 64) dbgz[tl * 64 + r0 + i] = valid ? xb[u] + yn[j] - T : -1;
                     }
                 }
-            });
+            }, dbgmode);
         }
+        const long long T2 = clock64();
         asm volatile("bar.sync 1, %0;" ::"n"(TC_CONS) : "memory");
+        const long long T3 = clock64();
         int n_live = scan ? 1 : 0, n_miss = 0, n_left = 0;
         if (scan) {
             const int fk = h->fk[side], ck = h->ck[side];
@@ -262,7 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_hist_kernel(TrackSet ts, con
                 n_miss = br.miss ? 1 : 0; n_left = br.done ? 0 : 1;
                 if (ORIENT == 1) {
                     int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
-                    rowpack[j] = make_int4(yn[j], br.lo - 2 * EPS, br.w + 4 * EPS, 0);
+                    rowpack[j] = pack_row(yn[j], br.lo, br.w);
                 }
                 if (!br.done && final_level) to_sparse(j);
             }
@@ -278,8 +354,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_hist_kernel(TrackSet ts, con
                 if (n_left) atomicAdd(&dbg[3], (unsigned)n_left);
             }
         }
+        if (prt && tid == 0) printf("hist CTA: begin %lld first_block %lld sweep_end %lld (%.0f per block) bar %lld scan_end %lld nblocks %d\n", T1 - T0, Tb1 - T0, T2 - T0, (double)(T2 - Tb1) / (nblocks - 1), T3 - T0, clock64() - T0, nblocks);
     }
     tc_end(tmem);
+    if (prt && tid == 0) printf("hist CTA total %lld\n", clock64() - T0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -288,14 +366,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_hist_kernel(TrackSet ts, con
 // "uncertain": inside a row or column bracket widened by 2 EPS, or near zero), one ballot per row = the CRP word of
 // the warp's 32 columns; uncertain cells are staged per lane and compacted to the pair's pool once per 32 rows.
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_STAGE = 32;                        // staged records per lane and half block (every cell fits)
+constexpr int TC_STAGE = 16;                        // staged records per lane and block (every cell of the warp's part fits)
 
-__global__ void __launch_bounds__(TC_THREADS, 2) tc_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n,
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n,
                                                                 FastLayout L, char *__restrict__ scratch, int groups, TcShift sh3,
                                                                 uint32_t *__restrict__ crp_all, int words, int64_t crp_words) {
     extern __shared__ __align__(128) unsigned char tc_raw[];
     TcSmem *s = reinterpret_cast<TcSmem *>(tc_raw);
-    uint2 *stage_all = reinterpret_cast<uint2 *>(tc_raw + sizeof(TcSmem));    // [8 warps][TC_STAGE][32 lanes]
+    uint2 *stage_all = reinterpret_cast<uint2 *>(tc_raw + sizeof(TcSmem));    // [consumer warp][TC_STAGE][32 lanes]
+    uint32_t *words_all = reinterpret_cast<uint32_t *>(stage_all + (size_t)(TC_CONS / 32) * TC_STAGE * 32);   // [consumer warp][16]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slot = blockIdx.x / groups, grp = blockIdx.x - slot * groups;
     if (slot >= n) return;
@@ -316,9 +395,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_emit_kernel(TrackSet ts, con
     const uint32_t tmem = tc_begin(s);
     const int nblocks = (Mx + TC_N - 1) / TC_N;
     if (tid >= TC_CONS) {
-        if (lane == 0)
-            tc_producer(s, slot_ptr<uint8_t>(scratch, L, slot, L.off_rpl), slot_ptr<uint8_t>(scratch, L, slot, L.off_qpl),
-                        (size_t)L.plane_frames * 16, cb, nblocks, tmem);
+        tc_producers(s, warp - TC_CONS / 32, lane, slot_ptr<uint8_t>(scratch, L, slot, L.off_rpl), slot_ptr<uint8_t>(scratch, L, slot, L.off_qpl),
+                     (size_t)L.plane_frames * 16, cb, nblocks, tmem);
     } else {
         const int32_t *yn = slot_ptr<int32_t>(scratch, L, slot, L.off_bbi);
         const int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
@@ -327,7 +405,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_emit_kernel(TrackSet ts, con
         uint2 *pool = slot_ptr<uint2>(scratch, L, slot, L.off_pool);
         uint32_t *pool_ctr = slot_ptr<uint32_t>(scratch, L, slot, L.off_pcnt);
         const unsigned pool_cap = (unsigned)L.pool_cap;
-        const int qd = warp & 3, hf = warp >> 2;
+        const int qd = warp & 3, part = warp >> 2;
         const int j = cb + qd * 32 + lane;                    // CRP column of this thread
         const bool valid = j < My;
         const int ynv = valid ? yn[j] : TC_HUGE;              // invalid: item huge => never in, never uncertain
@@ -336,29 +414,49 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_emit_kernel(TrackSet ts, con
         const unsigned jrec = (unsigned)j << 14;
         const int wcol = w_first + qd;                        // CRP word of this warp's 32 columns
         uint2 *stage = stage_all + (size_t)warp * TC_STAGE * 32 + lane;
+        const uint32_t stage0 = smem_u32(stage);
+        uint32_t *wrow = words_all + warp * 16;                // the 16 CRP words of this warp's part (lane 0 writes, lanes < 16 read)
+        const uint32_t wrow0 = smem_u32(wrow);
+        if (warp < 4) tc_fill_owned(s, tmem, warp, lane);
         for (int b = 0; b < nblocks; ++b) {
-            unsigned word = 0u, ns = 0u;
+            uint32_t sp = stage0;                              // next free staging entry of this lane (256 B apart)
+            if (lane < 2 && b + 1 < nblocks) tc_prefetch_l1(rowpack + (b + 1) * TC_N + part * 16 + 8 * lane);   // next block's 16 rows (256 B)
             tc_consume_block(s, tmem, b, warp, [&](int r0, const int (&v0)[16], const int (&v1)[16], const int (&v2)[16]) {
+                const unsigned rec0 = (unsigned)r0 | jrec;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int4 rp = __ldg(rowpack + r0 + i);  // {aa_fix, rowLo - 2 EPS, rowW + 4 EPS, -}
-                    const int T = (v0[i] << sh3.s0) + (v1[i] >> sh3.s1) + (v2[i] >> sh3.s2);
-                    const int ar = rp.x - rp.y + ynv - T;
+                    const int4 rp = __ldg(rowpack + r0 + i);  // pack_row(..)
+                    const int T = tc_item(v0[i], v1[i], v2[i], sh3);
+                    const int ar = rp.w + ynv - T;
                     const int ac = rp.x + ycl - T;
-                    const bool unc = ((unsigned)ar <= (unsigned)(rp.z - 1)) || ((unsigned)ac <= cw1) || (ar < 2 * EPS - rp.y);
                     const unsigned bal = __ballot_sync(0xffffffffu, (ar & ac) < 0);
-                    if (lane == ((r0 + i) & 31)) word = bal;
-                    if (unc) {
-                        stage[ns * 32] = make_uint2((unsigned)(r0 + i) | jrec, (unsigned)(ar + rp.y));
-                        ++ns;
-                    }
+                    // lane 0: the row's word; every lane: the record (cell, ar) of an uncertain cell (row zone, column zone or
+                    // near zero), predicated (a branch per cell would split the unrolled block into thousands of paths)
+                    asm volatile(
+                        "{\n"
+                        ".reg .pred p, q;\n"
+                        "setp.eq.u32 q, %8, 0;\n"
+                        "@q st.shared.u32 [%9], %10;\n"
+                        "setp.lt.u32 p, %1, %2;\n"
+                        "setp.le.u32 q, %3, %4;\n"
+                        "or.pred p, p, q;\n"
+                        "setp.lt.s32 q, %1, %5;\n"
+                        "or.pred p, p, q;\n"
+                        "@p st.shared.v2.u32 [%0], {%6, %1};\n"
+                        "@p add.u32 %0, %0, %7;\n"
+                        "}\n"
+                        : "+r"(sp)
+                        : "r"(ar), "r"(rp.z), "r"(ac), "r"(cw1), "r"(rp.y), "r"(rec0 + (unsigned)i), "n"(256), "r"(lane),
+                          "r"(wrow0 + 4u * (unsigned)i), "r"(bal)
+                        : "memory");
                 }
             });
-            // lane l holds the word of row b * 64 + hf * 32 + l
-            const int row = b * TC_N + hf * 32 + lane;
-            if (row < Mx && wcol < words) crp[(int64_t)row * words + wcol] = word;
-            if (__any_sync(0xffffffffu, ns != 0u)) {
-                const unsigned cnt = ns;
+            // lane l < 16 holds the word of row b * TC_N + 16 part + l
+            __syncwarp();
+            const int row = b * TC_N + part * 16 + lane;
+            if (lane < 16 && row < Mx && wcol < words) crp[(int64_t)row * words + wcol] = wrow[lane];
+            const unsigned cnt = (sp - stage0) >> 8;
+            if (__any_sync(0xffffffffu, cnt != 0u)) {          // staged records -> the pair's pool: one atomic per warp
                 unsigned incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -372,6 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_emit_kernel(TrackSet ts, con
                 for (unsigned e = 0; e < cnt; ++e)
                     if (base + e < pool_cap) pool[base + e] = stage[e * 32];
             }
+            __syncwarp();
         }
     }
     tc_end(tmem);
@@ -462,7 +561,7 @@ __global__ void __launch_bounds__(32 * WPC, 2) tc_sparse_kernel(TrackSet ts, con
             tc_load_limbs(X, L.plane_frames, fx, xc);
             if (a >= HALO && a < nrows) {                     // row a - 8 is complete (slot (U + 1) % 9)
                 constexpr int S = (U + 1) % M9;
-                const int T = (int)(a0[S] << sh3.s0) + (int)(a1[S] >> sh3.s1) + (int)(a2[S] >> sh3.s2);
+                const int T = tc_item((int)a0[S], (int)a1[S], (int)a2[S], sh3);
                 const int zr = __ldg(xn + a - HALO) + yrel - T;
                 const int idx = __vimin_s32_relu(zr >> shl, NBIN + 1);
                 atomicAdd(&hist[idx * 32], 1u);
@@ -490,7 +589,7 @@ __global__ void __launch_bounds__(32 * WPC, 2) tc_sparse_kernel(TrackSet ts, con
             else {
                 lo = br.lo; sh = br.sh;
                 lo_a[j] = br.lo; w_a[j] = br.w; cb_a[j] = br.below; sh_a[j] = br.done ? -1 : br.sh;
-                if (side == 0) slot_ptr<int4>(scratch, L, slot, L.off_rowpack)[j] = make_int4(ynj, br.lo - 2 * EPS, br.w + 4 * EPS, 0);
+                if (side == 0) slot_ptr<int4>(scratch, L, slot, L.off_rowpack)[j] = pack_row(ynj, br.lo, br.w);
                 if (br.done) livel = false;
             }
         }

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t *__restrict__ 
                                                     int reps, long long *__restrict__ cycles, int mode) {
     __shared__ Smem s;
     const int tid = threadIdx.x, warp = tid >> 5;
+    if (mode == 3) mode = (blockIdx.x >= gridDim.x / 2) ? 2 : 1;   // concurrency test: first half of the grid issues MMAs, second half reads TMEM
     for (int i = tid; i < NPL * AF * 16; i += 128) (&s.a[0][0][0])[i] = ga[i];
     for (int i = tid; i < NPL * BF * 16; i += 128) (&s.b[0][0][0])[i] = gb[i];
     for (int i = tid; i < N * 16; i += 128) (&s.zero[0][0])[i] = 0;
@@ -194,7 +195,7 @@ int main() {
         printf("\n");
     }
     // timing: one CTA alone, then one CTA per SM, then 4 CTAs per SM (TMEM: 4 x 128... this probe allocates 256 => 2 per SM)
-    for (int mode = 0; mode < 3; ++mode)
+    for (int mode = 0; mode < 4; ++mode)
     for (int grid : {1, 148, 296}) {
         const int reps = 200;
         probe_kernel<<<grid, 128>>>(da, db, dout, reps, dc, mode);
@@ -203,6 +204,11 @@ int main() {
         std::vector<long long> cyc(grid);
         cudaMemcpy(cyc.data(), dc, grid * 8, cudaMemcpyDeviceToHost);
         long long mx = 0; for (auto c : cyc) mx = c > mx ? c : mx;
+        if (mode == 3 && grid == 296) {
+            long long m1 = 0, m2 = 0;
+            for (int i = 0; i < 148; ++i) { m1 = cyc[i] > m1 ? cyc[i] : m1; m2 = cyc[148 + i] > m2 ? cyc[148 + i] : m2; }
+            printf("mode 3 grid 296: MMA-only CTAs %.0f cycles per block, ld-only CTAs %.0f cycles per block (sharing SMs)\n", (double)m1 / reps, (double)m2 / reps);
+        }
         printf("mode %d (0 full, 1 MMA only, 2 ld only) grid %d: %.0f cycles per 128x%d block, %.2f cells/clk/CTA\n", mode, grid, (double)mx / reps, N,
                (double)M * N * reps / mx);
     }
