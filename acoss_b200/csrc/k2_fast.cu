@@ -58,8 +58,8 @@ constexpr int RCV = 4;              // owned frames per lane (register columns) 
 #ifndef K2_HMINB
 #define K2_HMINB K2_MINB            // CTAs per SM the histogram sweeps are compiled for
 #endif
-#ifndef K2_TC
-#define K2_TC 1                     // 1: histogram / emit sweeps and the sparse level on the tensor cores (k2_tc.inl)
+#ifndef K2_TC_MIN_WINDOWS
+#define K2_TC_MIN_WINDOWS 1000       // longer side of the matrix from which the tensor sweeps (k2_tc.inl) replace the FFMA2 sweeps
 #endif
 #ifndef K2_MINB
 #define K2_MINB 3                   // CTAs per SM the sweep kernels are compiled for (register cap 168 at 3, 255 at 2)
@@ -1551,7 +1551,7 @@ __global__ void collect_fallback_kernel(const uint32_t *__restrict__ status, int
 // host side
 // ------------------------------------------------------------------------------------------------
 bool k2_fast_supported(const acoss_params &p, const SlotGeom &g, const TrackSet &ts) {
-    return p.m == M9 && p.tau == 1 && ts.fx_exp > -100 && ts.nonneg && (!K2_TC || ts.q_exp >= 0) && g.max_rows < 16000 && g.max_cols < 16000 &&
+    return p.m == M9 && p.tau == 1 && ts.fx_exp > -100 && ts.nonneg && g.max_rows < 16000 && g.max_cols < 16000 &&
            g.max_rows >= 2 && g.max_cols >= 2;
 }
 
@@ -1575,7 +1575,14 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     auto tb = [&](int id) { if (timer) timer->begin(id); };
     auto te = [&](int id) { if (timer) timer->end(id); };
     tb(K2K_PREP);
-    const float q_scale = ts.q_exp >= 0 ? ldexpf(1.f, ts.q_exp) : 0.f;
+    // Sweeps: tensor cores from K2_TC_MIN_WINDOWS windows on the longer side (a CTA's fixed costs - TMEM allocation, operand
+    // fill, histogram scan - weigh on short lines; measured: +17 % at 2 000 frames, -5 % at 500), FFMA2 below and whenever the
+    // features cannot be quantised.  ACOSS_K2_SWEEPS=tc|ffma forces one of them (A/B runs, parity tests of both).
+    const char *sweeps_env = getenv("ACOSS_K2_SWEEPS");          // read per call: tests flip it inside one process
+    bool use_tc = ts.q_exp >= 0 && std::max(g.max_rows, g.max_cols) >= K2_TC_MIN_WINDOWS;
+    if (sweeps_env && sweeps_env[0] == 't') use_tc = ts.q_exp >= 0;
+    if (sweeps_env && sweeps_env[0] == 'f') use_tc = false;
+    const float q_scale = use_tc ? ldexpf(1.f, ts.q_exp) : 0.f;
     fast_prep_kernel<<<n, 256, 0, st>>>(ts, pairs, oti, first, L, base, qperc, p.integer_guard, fx_scale, q_scale);
     CUDA_TRY(cudaGetLastError());
     te(K2K_PREP);
@@ -1616,8 +1623,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     // two dense levels per orientation: the second sweeps only strips that still hold DENSE2_MIN_LIVE or more live
     // lines (short lines start from the whole item range and need it; ordinary strips skip it at once) and hands
     // every line still live to the sparse refinement
-#if K2_TC
-    {
+    if (use_tc) {
         // tensor sweeps (k2_tc.inl): one CTA = 128 owned lines; items from tcgen05.mma.kind::i8 over the byte planes
         const int e0 = 56 - 2 * ts.q_exp - ts.fx_exp;
         const TcShift sh3 = {e0, 8 - e0, 16 - e0, 1u << e0};
@@ -1633,18 +1639,17 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
             tc_attr_done[dev & 63] = true;
         }
         const unsigned tgc = (unsigned)((int64_t)n * tstrips_c), tgr = (unsigned)((int64_t)n * tstrips_r);
-        static const int tcdbg = getenv("ACOSS_TC_DBG") ? atoi(getenv("ACOSS_TC_DBG")) : 0;
         tb(K2K_HIST_COL);
-        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg, 1, 0, glive, gcap, tcdbg);
+        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg, 1, 0, glive, gcap);
         te(K2K_HIST_COL);
         tb(K2K_HIST_ROW);
-        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 4, 1, 0, glive, gcap, tcdbg);
+        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 4, 1, 0, glive, gcap);
         te(K2K_HIST_ROW);
         tb(K2K_HIST_COL2);
-        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap, 0);
+        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap);
         te(K2K_HIST_COL2);
         tb(K2K_HIST_ROW2);
-        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap, 0);
+        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap);
         CUDA_TRY(cudaGetLastError());
         te(K2K_HIST_ROW2);
         const int64_t warps = ((int64_t)gcap + 31) / 32;
@@ -1657,8 +1662,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
         tc_emit_kernel<<<(unsigned)((int64_t)n * groups), TC_THREADS, smem_e, st>>>(ts, pairs, first, n, L, base, groups, sh3, crp, g.words, g.crp_words);
         CUDA_TRY(cudaGetLastError());
         te(K2K_EMIT);
-    }
-#else
+    } else {
     tb(K2K_HIST_COL);
     fast_hist_kernel<HRC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_c, magic, status, dbg, 1, 0, glive, gcap);
     te(K2K_HIST_COL);
@@ -1666,10 +1670,10 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     fast_hist_kernel<HRC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_r, magic, status, dbg + 4, 1, 0, glive, gcap);
     te(K2K_HIST_ROW);
     tb(K2K_HIST_COL2);
-    fast_hist_kernel<HRC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap, 0);
+    fast_hist_kernel<HRC, 0><<<gc, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_c, magic, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap);
     te(K2K_HIST_COL2);
     tb(K2K_HIST_ROW2);
-    fast_hist_kernel<HRC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap, 0);
+    fast_hist_kernel<HRC, 1><<<gr, 32 * WPC, smem, st>>>(ts, pairs, first, n, L, base, hstrips_r, magic, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap);
     CUDA_TRY(cudaGetLastError());
     te(K2K_HIST_ROW2);
     {
@@ -1690,7 +1694,7 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
         CUDA_TRY(cudaGetLastError());
         te(K2K_EMIT);
     }
-#endif
+    }
     tb(K2K_SCATTER);
     fast_scatter_kernel<<<dim3((L.pool_cap + SCAT_CHUNK - 1) / SCAT_CHUNK, n), 256, 0, st>>>(n, L, base, first, status, dbg);
     CUDA_TRY(cudaGetLastError());

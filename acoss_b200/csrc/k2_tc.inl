@@ -200,34 +200,17 @@ __device__ __forceinline__ void tc_end(uint32_t tmem) {
     if (threadIdx.x >= TC_CONS && threadIdx.x < TC_CONS + 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
 }
 
-// mbarrier wait of the consumer warps: polls back off so that twenty waiting warps do not fight the MMA's operand reads for
-// shared-memory bandwidth
-__device__ __forceinline__ void tc_wait_sleep(unsigned long long *b, uint32_t parity) {
-    uint32_t done = 0;
-    for (;;) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(200);
-    }
-}
-
 __device__ __forceinline__ void tc_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Consumer side of one block: fn(first_window, acc0[16], acc1[16], acc2[16]) for this warp's 16 windows.  The accumulator
 // buffer is released (acc_free) as soon as the values sit in registers.
 template <typename Fn>
-__device__ __forceinline__ void tc_consume_block(TcSmem *s, uint32_t tmem, int b, int warp, Fn &&fn, int dbgmode = 0) {
+__device__ __forceinline__ void tc_consume_block(TcSmem *s, uint32_t tmem, int b, int warp, Fn &&fn) {
     const int buf = b & 1;
-    tc_wait_sleep(&s->acc_full[buf], (uint32_t)((b >> 1) & 1));
+    mbar_wait(&s->acc_full[buf], (uint32_t)((b >> 1) & 1));
     tc_fence_after();
     const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * TC_BUF + (warp >> 2) * 16);
     int v0[16], v1[16], v2[16];
-    if (dbgmode == 4) {
-        tc_fence_before();
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&s->acc_free[buf]);
-        return;
-    }
     tc_ld16(tbase, v0);
     tc_ld16(tbase + TC_N, v1);
     tc_ld16(tbase + 2 * TC_N, v2);
@@ -246,7 +229,7 @@ template <int ORIENT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n,
                                                                 FastLayout L, char *__restrict__ scratch, int strips_max, TcShift sh3,
                                                                 uint32_t *__restrict__ status, uint32_t *__restrict__ dbg, int min_live,
-                                                                int final_level, uint32_t *__restrict__ glive, uint32_t gcap, int dbgmode) {
+                                                                int final_level, uint32_t *__restrict__ glive, uint32_t gcap) {
     extern __shared__ __align__(128) unsigned char tc_raw[];
     TcSmem *s = reinterpret_cast<TcSmem *>(tc_raw);
     uint32_t *hist = reinterpret_cast<uint32_t *>(tc_raw + sizeof(TcSmem));   // [NBIN + 2][128]
@@ -289,11 +272,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
         if (scan) to_sparse(j);
         return;
     }
-    const long long T0 = clock64();
-    const bool prt = (dbgmode >= 8) && blockIdx.x == 5000;
     for (int i = tid; i < (NBIN + 2) * 128; i += TC_THREADS) hist[i] = 0u;
     const uint32_t tmem = tc_begin(s);
-    const long long T1 = clock64();
     const int nblocks = (Mxs + TC_N - 1) / TC_N;
     if (!cons) {
         const uint8_t *qpl = slot_ptr<uint8_t>(scratch, L, slot, L.off_qpl), *rpl = slot_ptr<uint8_t>(scratch, L, slot, L.off_rpl);
@@ -301,14 +281,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
     } else {
         if (warp < 4) tc_fill_owned(s, tmem, warp, lane);
         uint32_t *hp = hist + tl;
-        long long Tb1 = 0;
         for (int b = 0; b < nblocks; ++b) {
-            if (b == 1) Tb1 = clock64();
             if (lane == 0 && b + 1 < nblocks) tc_prefetch_l1(xn + (b + 1) * TC_N + (warp >> 2) * 16);   // next block's 16 norms (64 B)
             tc_consume_block(s, tmem, b, warp, [&](int r0, const int (&v0)[16], const int (&v1)[16], const int (&v2)[16]) {
                 const int4 *xp = reinterpret_cast<const int4 *>(xn + r0);
-                if (dbgmode == 2) { if (v0[0] + v1[3] + v2[7] == 0x12345678) atomicAdd(&hp[0], 1u); return; }
-                if (dbgmode == 3) { int a = 0; for (int g = 0; g < 4; ++g) { const int4 xv = __ldg(xp + g); a += xv.x + xv.y + xv.z + xv.w; } for (int i = 0; i < 16; ++i) a += tc_item(v0[i], v1[i], v2[i], sh3) >> shf; if (a == 0x12345678) atomicAdd(&hp[0], 1u); return; }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const int4 xv = __ldg(xp + g);
@@ -321,11 +297,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
                         atomicAdd(&hp[idx * 128], 1u);
                     }
                 }
-            }, dbgmode);
+            });
         }
-        const long long T2 = clock64();
         asm volatile("bar.sync 1, %0;" ::"n"(TC_CONS) : "memory");
-        const long long T3 = clock64();
         int n_live = scan ? 1 : 0, n_miss = 0, n_left = 0;
         if (scan) {
             const int fk = h->fk[side], ck = h->ck[side];
@@ -354,10 +328,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
                 if (n_left) atomicAdd(&dbg[3], (unsigned)n_left);
             }
         }
-        if (prt && tid == 0) printf("hist CTA: begin %lld first_block %lld sweep_end %lld (%.0f per block) bar %lld scan_end %lld nblocks %d\n", T1 - T0, Tb1 - T0, T2 - T0, (double)(T2 - Tb1) / (nblocks - 1), T3 - T0, clock64() - T0, nblocks);
     }
     tc_end(tmem);
-    if (prt && tid == 0) printf("hist CTA total %lld\n", clock64() - T0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,7 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
 // "uncertain": inside a row or column bracket widened by 2 EPS, or near zero), one ballot per row = the CRP word of
 // the warp's 32 columns; uncertain cells are staged per lane and compacted to the pair's pool once per 32 rows.
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_STAGE = 16;                        // staged records per lane and block (every cell of the warp's part fits)
+constexpr int TC_STAGE = 32;                        // staged records per lane between two flushes (two blocks: every cell fits)
 
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_emit_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n,
                                                                 FastLayout L, char *__restrict__ scratch, int groups, TcShift sh3,
@@ -418,8 +390,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_emit_kernel(TrackSet ts, con
         uint32_t *wrow = words_all + warp * 16;                // the 16 CRP words of this warp's part (lane 0 writes, lanes < 16 read)
         const uint32_t wrow0 = smem_u32(wrow);
         if (warp < 4) tc_fill_owned(s, tmem, warp, lane);
+        uint32_t sp = stage0;                                  // next free staging entry of this lane (256 B apart)
         for (int b = 0; b < nblocks; ++b) {
-            uint32_t sp = stage0;                              // next free staging entry of this lane (256 B apart)
             if (lane < 2 && b + 1 < nblocks) tc_prefetch_l1(rowpack + (b + 1) * TC_N + part * 16 + 8 * lane);   // next block's 16 rows (256 B)
             tc_consume_block(s, tmem, b, warp, [&](int r0, const int (&v0)[16], const int (&v1)[16], const int (&v2)[16]) {
                 const unsigned rec0 = (unsigned)r0 | jrec;
@@ -455,7 +427,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_emit_kernel(TrackSet ts, con
             __syncwarp();
             const int row = b * TC_N + part * 16 + lane;
             if (lane < 16 && row < Mx && wcol < words) crp[(int64_t)row * words + wcol] = wrow[lane];
+            if (!(b & 1) && b + 1 < nblocks) { __syncwarp(); continue; }   // flush every second block
             const unsigned cnt = (sp - stage0) >> 8;
+            sp = stage0;
             if (__any_sync(0xffffffffu, cnt != 0u)) {          // staged records -> the pair's pool: one atomic per warp
                 unsigned incl = cnt;
 #pragma unroll
