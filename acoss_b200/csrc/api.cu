@@ -272,13 +272,16 @@ static int finish_tracks(acoss_ctx *c, const int64_t *offsets, int32_t n_tracks,
         c->fx_exp = e;
     }
     if (((uintptr_t)c->d_frames & 15) != 0) c->fx_exp = -1000;   // vector loads need 16 B alignment
-    // tensor sweeps: 24-bit quantisation x_q = rint(x * 2^q_exp) < 2^24 of the non-negative features
+    // tensor sweeps: 24-bit quantisation x_q = rint(x * 2^q_exp) < 2^24 of the non-negative features.  The limb products the
+    // sweeps keep weigh 2^e0, 2^(e0 - 8), 2^(e0 - 16) fixed-point units; their error against the exact item grows with e0
+    // (quantisation 1.4 * 2^(e0/2) units, dropped limb products 0.84 * 2^e0: DESIGN.md 4.2), so e0 <= 6 keeps it inside EPS
+    // (HPCP: frames normalised to max 1, largest squared frame norm in [4, 16)  =>  e0 = 5 or 6).
     c->q_exp = -1;
     if (c->fx_exp > -100 && c->nonneg && st2[2] > 0.f) {
         int e = 0;
         frexp((double)st2[2] * 1.000001, &e);        // max feature < 2^e / 1.000001  =>  rint(x * 2^(24 - e)) <= 2^24 - 2
-        const int qe = 24 - e, e0 = 56 - 2 * qe - c->fx_exp;   // limb-product weights in fixed-point units: 2^e0, 2^(e0 - 8), 2^(e0 - 16)
-        if (e0 >= 0 && e0 <= 8) c->q_exp = qe;
+        const int qe = 24 - e, e0 = 56 - 2 * qe - c->fx_exp;
+        if (e0 >= 0 && e0 <= 6) c->q_exp = qe;
     }
     return ACOSS_OK;
 }
