@@ -59,7 +59,7 @@ constexpr int RCV = 4;              // owned frames per lane (register columns) 
 #define K2_HMINB K2_MINB            // CTAs per SM the histogram sweeps are compiled for
 #endif
 #ifndef K2_TC_MIN_WINDOWS
-#define K2_TC_MIN_WINDOWS 1000       // longer side of the matrix from which the tensor sweeps (k2_tc.inl) replace the FFMA2 sweeps
+#define K2_TC_MIN_WINDOWS 400        // longer side of the matrix from which the tensor sweeps (k2_tc.inl) replace the FFMA2 sweeps
 #endif
 #ifndef K2_MINB
 #define K2_MINB 3                   // CTAs per SM the sweep kernels are compiled for (register cap 168 at 3, 255 at 2)
@@ -1576,8 +1576,8 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
     auto te = [&](int id) { if (timer) timer->end(id); };
     tb(K2K_PREP);
     // Sweeps: tensor cores from K2_TC_MIN_WINDOWS windows on the longer side (a CTA's fixed costs - TMEM allocation, operand
-    // fill, histogram scan - weigh on short lines; measured: +17 % at 2 000 frames, -5 % at 500), FFMA2 below and whenever the
-    // features cannot be quantised.  ACOSS_K2_SWEEPS=tc|ffma forces one of them (A/B runs, parity tests of both).
+    // fill, histogram scan - weigh on short lines; measured against the FFMA2 sweeps: +17 % pairs/s at 2 000 frames, level at
+    // 500), FFMA2 below and whenever the features cannot be quantised within the error budget.  ACOSS_K2_SWEEPS=tc|ffma forces one of them (A/B runs, parity tests of both).
     const char *sweeps_env = getenv("ACOSS_K2_SWEEPS");          // read per call: tests flip it inside one process
     bool use_tc = ts.q_exp >= 0 && std::max(g.max_rows, g.max_cols) >= K2_TC_MIN_WINDOWS;
     if (sweeps_env && sweeps_env[0] == 't') use_tc = ts.q_exp >= 0;
@@ -1639,19 +1639,14 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
             tc_attr_done[dev & 63] = true;
         }
         const unsigned tgc = (unsigned)((int64_t)n * tstrips_c), tgr = (unsigned)((int64_t)n * tstrips_r);
+        // one launch per orientation: a CTA that still holds DENSE2_MIN_LIVE live lines after its sweep sweeps again at once
         tb(K2K_HIST_COL);
-        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg, 1, 0, glive, gcap);
+        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg, dbg + 12, glive, gcap);
         te(K2K_HIST_COL);
         tb(K2K_HIST_ROW);
-        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 4, 1, 0, glive, gcap);
-        te(K2K_HIST_ROW);
-        tb(K2K_HIST_COL2);
-        tc_hist_kernel<0><<<tgc, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_c, sh3, status, dbg + 12, DENSE2_MIN_LIVE, 1, glive, gcap);
-        te(K2K_HIST_COL2);
-        tb(K2K_HIST_ROW2);
-        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 16, DENSE2_MIN_LIVE, 1, glive, gcap);
+        tc_hist_kernel<1><<<tgr, TC_THREADS, smem_h, st>>>(ts, pairs, first, n, L, base, tstrips_r, sh3, status, dbg + 4, dbg + 16, glive, gcap);
         CUDA_TRY(cudaGetLastError());
-        te(K2K_HIST_ROW2);
+        te(K2K_HIST_ROW);
         const int64_t warps = ((int64_t)gcap + 31) / 32;
         tb(K2K_SPARSE);
         tc_sparse_kernel<<<(unsigned)((warps + WPC - 1) / WPC), 32 * WPC, 0, st>>>(ts, pairs, first, n, L, base, sh3, status, dbg + 8, glive, gcap);

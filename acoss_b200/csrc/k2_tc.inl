@@ -38,8 +38,9 @@ struct alignas(128) TcSmem {
     uint8_t a[3][TC_AF][16];                        // owned planes h, l1, l2
     uint8_t b[TC_BST][3][TC_BF][16];                // streamed planes
     uint8_t zero[TC_N][16];
-    unsigned long long afull, aready, bfull[TC_BST], bfree[TC_BST], acc_full[2], acc_free[2];
+    unsigned long long afull, aready, bfull[TC_BST], bfree[TC_BST], acc_full[2], acc_free[2], lvl;
     uint32_t tmem_base;
+    int go, nleft;                                  // histogram sweeps: sweep again? / lines still live after a level
 };
 
 // 2 <X, Y> in fixed-point units from the three limb-product accumulators (one floor; the same expression in every kernel)
@@ -139,38 +140,52 @@ __device__ __forceinline__ void tc_fill_owned(TcSmem *s, uint32_t tmem, int warp
 // stages).  Two MMA issuers, one per accumulator buffer (even / odd blocks): while one waits for its buffer or commits, the
 // other keeps the tensor pipe fed (a single issuer spends a third of its time in barrier waits and copy issue).
 __device__ __forceinline__ void tc_loader(TcSmem *s, const uint8_t *__restrict__ own, const uint8_t *__restrict__ str, size_t plane_bytes,
-                                          int own_first, int nblocks) {
+                                          int own_first, int nblocks, int max_levels) {
     mbar_expect_tx(&s->afull, 3 * TC_ALOAD * 16);
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) bulk_g2s(&s->a[pl][0][0], own + pl * plane_bytes + (size_t)own_first * 16, TC_ALOAD * 16, &s->afull);
-    for (int b = 0; b < nblocks; ++b) {
-        const int st = b % TC_BST;
-        if (b >= TC_BST) mbar_wait(&s->bfree[st], (uint32_t)((b / TC_BST - 1) & 1));   // the MMAs of block b - 3 have read the stage
-        mbar_expect_tx(&s->bfull[st], 3 * TC_BF * 16);
+    for (int level = 0, g = 0; level < max_levels; ++level) {
+        if (level > 0) {                                                  // another sweep only if the consumers ask for it
+            mbar_wait(&s->lvl, (uint32_t)((level - 1) & 1));
+            if (!s->go) return;
+        }
+        for (int b = 0; b < nblocks; ++b, ++g) {
+            const int st = g % TC_BST;
+            if (g >= TC_BST) mbar_wait(&s->bfree[st], (uint32_t)((g / TC_BST - 1) & 1));   // the MMAs of block g - 3 have read the stage
+            mbar_expect_tx(&s->bfull[st], 3 * TC_BF * 16);
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl)
-            bulk_g2s(&s->b[st][pl][0][0], str + pl * plane_bytes + (size_t)b * TC_N * 16, TC_BF * 16, &s->bfull[st]);
+            for (int pl = 0; pl < 3; ++pl)
+                bulk_g2s(&s->b[st][pl][0][0], str + pl * plane_bytes + (size_t)b * TC_N * 16, TC_BF * 16, &s->bfull[st]);
+        }
     }
 }
-__device__ __forceinline__ void tc_issuer(TcSmem *s, int buf, int nblocks, uint32_t tmem) {
+__device__ __forceinline__ void tc_issuer(TcSmem *s, int buf, int nblocks, int max_levels, uint32_t tmem) {
     mbar_wait(&s->aready, 0);
     const uint32_t zero = smem_u32(&s->zero[0][0]);
-    for (int b = buf; b < nblocks; b += 2) {
-        const int st = b % TC_BST;
-        mbar_wait(&s->bfull[st], (uint32_t)((b / TC_BST) & 1));
-        if (b >= 2) mbar_wait(&s->acc_free[buf], (uint32_t)(((b >> 1) - 1) & 1));   // consumers hold block b - 2 in registers
-        tc_fence_after();
-        tc_issue_block(smem_u32(&s->b[st][0][0][0]), zero, tmem, buf * TC_BUF);
-        tc_commit(&s->acc_full[buf]);
-        tc_commit(&s->bfree[st]);
+    for (int level = 0; level < max_levels; ++level) {
+        if (level > 0) {
+            mbar_wait(&s->lvl, (uint32_t)((level - 1) & 1));
+            if (!s->go) return;
+        }
+        for (int g = level * nblocks; g < (level + 1) * nblocks; ++g) {
+            if ((g & 1) != buf) continue;
+            const int st = g % TC_BST;
+            mbar_wait(&s->bfull[st], (uint32_t)((g / TC_BST) & 1));
+            if (g >= 2) mbar_wait(&s->acc_free[buf], (uint32_t)(((g >> 1) - 1) & 1));   // consumers hold block g - 2 in registers
+            tc_fence_after();
+            tc_issue_block(smem_u32(&s->b[st][0][0][0]), zero, tmem, buf * TC_BUF);
+            tc_commit(&s->acc_full[buf]);
+            tc_commit(&s->bfree[st]);
+        }
     }
 }
-// role dispatch of the three producer warps (warp index relative to the first producer warp)
+// role dispatch of the three producer warps (warp index relative to the first producer warp).  max_levels > 1: after a sweep
+// the producers wait for the consumers' decision (lvl barrier, s->go) whether the CTA sweeps again.
 __device__ __forceinline__ void tc_producers(TcSmem *s, int pwarp, int lane, const uint8_t *__restrict__ own, const uint8_t *__restrict__ str,
-                                             size_t plane_bytes, int own_first, int nblocks, uint32_t tmem) {
+                                             size_t plane_bytes, int own_first, int nblocks, uint32_t tmem, int max_levels = 1) {
     if (lane != 0) return;
-    if (pwarp == 2) tc_loader(s, own, str, plane_bytes, own_first, nblocks);
-    else tc_issuer(s, pwarp, nblocks, tmem);
+    if (pwarp == 2) tc_loader(s, own, str, plane_bytes, own_first, nblocks, max_levels);
+    else tc_issuer(s, pwarp, nblocks, max_levels, tmem);
 }
 
 // Common CTA prologue / epilogue: barriers, zero block, TMEM allocation by the producer warp.
@@ -180,6 +195,8 @@ __device__ __forceinline__ uint32_t tc_begin(TcSmem *s) {
     if (tid == 0) {
         mbar_init(&s->afull, 1);
         mbar_init(&s->aready, 4);
+        mbar_init(&s->lvl, 1);
+        s->go = 0; s->nleft = 0;
         for (int i = 0; i < TC_BST; ++i) { mbar_init(&s->bfull[i], 1); mbar_init(&s->bfree[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&s->acc_full[i], 1); mbar_init(&s->acc_free[i], TC_CONS / 32); }
         mbar_fence_init();
@@ -205,9 +222,9 @@ __device__ __forceinline__ void tc_prefetch_l1(const void *p) { asm volatile("pr
 // Consumer side of one block: fn(first_window, acc0[16], acc1[16], acc2[16]) for this warp's 16 windows.  The accumulator
 // buffer is released (acc_free) as soon as the values sit in registers.
 template <typename Fn>
-__device__ __forceinline__ void tc_consume_block(TcSmem *s, uint32_t tmem, int b, int warp, Fn &&fn) {
-    const int buf = b & 1;
-    mbar_wait(&s->acc_full[buf], (uint32_t)((b >> 1) & 1));
+__device__ __forceinline__ void tc_consume_block(TcSmem *s, uint32_t tmem, int g, int b, int warp, Fn &&fn) {   // g: running block index
+    const int buf = g & 1;
+    mbar_wait(&s->acc_full[buf], (uint32_t)((g >> 1) & 1));
     tc_fence_after();
     const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * TC_BUF + (warp >> 2) * 16);
     int v0[16], v1[16], v2[16];
@@ -228,8 +245,8 @@ __device__ __forceinline__ void tc_consume_block(TcSmem *s, uint32_t tmem, int b
 template <int ORIENT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, const int32_t *__restrict__ pairs, int64_t first, int n,
                                                                 FastLayout L, char *__restrict__ scratch, int strips_max, TcShift sh3,
-                                                                uint32_t *__restrict__ status, uint32_t *__restrict__ dbg, int min_live,
-                                                                int final_level, uint32_t *__restrict__ glive, uint32_t gcap) {
+                                                                uint32_t *__restrict__ status, uint32_t *__restrict__ dbg,
+                                                                uint32_t *__restrict__ dbg2, uint32_t *__restrict__ glive, uint32_t gcap) {
     extern __shared__ __align__(128) unsigned char tc_raw[];
     TcSmem *s = reinterpret_cast<TcSmem *>(tc_raw);
     uint32_t *hist = reinterpret_cast<uint32_t *>(tc_raw + sizeof(TcSmem));   // [NBIN + 2][128]
@@ -254,79 +271,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
     const bool cons = tid < TC_CONS;
     const int tl = (warp & 3) * 32 + lane;                    // owned line within the CTA (consumers)
     const int j = cb + tl;
-    bool valid = cons && j < My;
-    const int shv = valid ? sh_a[j] : -1;
-    if (shv < 0) valid = false;
-    const int shf = valid ? shv : 0;
-    // bin = ((z - lo) >> sh) + 1 clamped to [0, NBIN + 1]; idle lines land in the overflow bin
-    const int ynrel = valid ? yn[j] - lo_a[j] + (1 << shv) : 0x40000000;
-    const bool scan = valid && warp < 4;                     // one thread per line scans (all parts count into one histogram)
-    const int n_live_cta = __syncthreads_count(scan);
-    if (n_live_cta == 0) return;
-    auto to_sparse = [&](int line) {
+    // a line is live while its bracket can still be split (shift >= 0 in sh_a; -1 = done)
+    bool valid = cons && j < My && sh_a[j] >= 0;
+    if (__syncthreads_count(valid && warp < 4) == 0) return;
+    auto to_sparse = [&](int line) {                          // the sparse level finishes it (call-wide list)
         const unsigned pos = atomicAdd(glive, 1u);
         if (pos < gcap) glive[1 + pos] = ((uint32_t)slot << 16) | ((uint32_t)side << 15) | (uint32_t)line;
-        else atomicOr(&status[k], PAIR_ST_FALLBACK | 8u);
+        else atomicOr(&status[k], PAIR_ST_FALLBACK | 8u);     // reason 8: too many crowded lines in this call
     };
-    if (n_live_cta < min_live) {
-        if (scan) to_sparse(j);
-        return;
-    }
     for (int i = tid; i < (NBIN + 2) * 128; i += TC_THREADS) hist[i] = 0u;
     const uint32_t tmem = tc_begin(s);
     const int nblocks = (Mxs + TC_N - 1) / TC_N;
+    constexpr int LEVELS = 2;                                 // dense levels a CTA may run back to back (operand tiles stay in TMEM)
     if (!cons) {
         const uint8_t *qpl = slot_ptr<uint8_t>(scratch, L, slot, L.off_qpl), *rpl = slot_ptr<uint8_t>(scratch, L, slot, L.off_rpl);
-        tc_producers(s, warp - TC_CONS / 32, lane, ORIENT == 0 ? rpl : qpl, ORIENT == 0 ? qpl : rpl, (size_t)L.plane_frames * 16, cb, nblocks, tmem);
+        tc_producers(s, warp - TC_CONS / 32, lane, ORIENT == 0 ? rpl : qpl, ORIENT == 0 ? qpl : rpl, (size_t)L.plane_frames * 16, cb, nblocks, tmem,
+                     LEVELS);
     } else {
         if (warp < 4) tc_fill_owned(s, tmem, warp, lane);
         uint32_t *hp = hist + tl;
-        for (int b = 0; b < nblocks; ++b) {
-            if (lane == 0 && b + 1 < nblocks) tc_prefetch_l1(xn + (b + 1) * TC_N + (warp >> 2) * 16);   // next block's 16 norms (64 B)
-            tc_consume_block(s, tmem, b, warp, [&](int r0, const int (&v0)[16], const int (&v1)[16], const int (&v2)[16]) {
-                const int4 *xp = reinterpret_cast<const int4 *>(xn + r0);
+        const int fk = h->fk[side], ck = h->ck[side];
+        for (int level = 0; level < LEVELS; ++level) {
+            const int shf = valid ? sh_a[j] : 0;
+            // bin = ((z - lo) >> sh) + 1 clamped to [0, NBIN + 1]; idle lines land in the overflow bin
+            const int ynrel = valid ? yn[j] - lo_a[j] + (1 << shf) : 0x40000000;
+            for (int b = 0; b < nblocks; ++b) {
+                if (lane == 0 && b + 1 < nblocks) tc_prefetch_l1(xn + (b + 1) * TC_N + (warp >> 2) * 16);   // next block's 16 norms (64 B)
+                tc_consume_block(s, tmem, level * nblocks + b, b, warp, [&](int r0, const int (&v0)[16], const int (&v1)[16], const int (&v2)[16]) {
+                    const int4 *xp = reinterpret_cast<const int4 *>(xn + r0);
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int4 xv = __ldg(xp + g);
-                    const int xb[4] = {xv.x, xv.y, xv.z, xv.w};
+                    for (int g = 0; g < 4; ++g) {
+                        const int4 xv = __ldg(xp + g);
+                        const int xb[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = 4 * g + u;
-                        const int zr = xb[u] + ynrel - tc_item(v0[i], v1[i], v2[i], sh3);
-                        const int idx = __vimin_s32_relu(zr >> shf, NBIN + 1);
-                        atomicAdd(&hp[idx * 128], 1u);
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = 4 * g + u;
+                            const int zr = xb[u] + ynrel - tc_item(v0[i], v1[i], v2[i], sh3);
+                            const int idx = __vimin_s32_relu(zr >> shf, NBIN + 1);
+                            atomicAdd(&hp[idx * 128], 1u);
+                        }
+                    }
+                });
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_CONS) : "memory");
+            // one thread per line scans (all parts counted into one histogram)
+            const bool scan = valid && warp < 4;
+            int n_live = scan ? 1 : 0, n_miss = 0, n_left = 0;
+            if (scan) {
+                const Bracket br = split_bracket<128>(hp, 0, 0xffffffffu, fk, ck, lo_a[j], shf, h->lo1, h->hi1, bracket_target(nX - M9));
+                if (br.bad) {                                 // cannot happen: the bins cover every item of the line
+                    atomicOr(&status[k], PAIR_ST_FALLBACK | 4u);
+                    sh_a[j] = -1;
+                    valid = false;
+                } else {
+                    lo_a[j] = br.lo; w_a[j] = br.w; cb_a[j] = br.below; sh_a[j] = br.done ? -1 : br.sh;
+                    n_miss = br.miss ? 1 : 0; n_left = br.done ? 0 : 1;
+                    if (ORIENT == 1) {
+                        int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
+                        rowpack[j] = pack_row(yn[j], br.lo, br.w);
                     }
                 }
-            });
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_CONS) : "memory");
-        int n_live = scan ? 1 : 0, n_miss = 0, n_left = 0;
-        if (scan) {
-            const int fk = h->fk[side], ck = h->ck[side];
-            const Bracket br = split_bracket<128>(hp, 0, 0xffffffffu, fk, ck, lo_a[j], shf, h->lo1, h->hi1, bracket_target(nX - M9));
-            if (br.bad) {
-                atomicOr(&status[k], PAIR_ST_FALLBACK | 4u);
-                sh_a[j] = -1;
-            } else {
-                lo_a[j] = br.lo; w_a[j] = br.w; cb_a[j] = br.below; sh_a[j] = br.done ? -1 : br.sh;
-                n_miss = br.miss ? 1 : 0; n_left = br.done ? 0 : 1;
-                if (ORIENT == 1) {
-                    int4 *rowpack = slot_ptr<int4>(scratch, L, slot, L.off_rowpack);
-                    rowpack[j] = pack_row(yn[j], br.lo, br.w);
+            }
+            uint32_t *dl = level == 0 ? dbg : dbg2;
+            if (warp < 4) {
+                n_live = __reduce_add_sync(0xffffffffu, n_live);
+                n_miss = __reduce_add_sync(0xffffffffu, n_miss);
+                n_left = __reduce_add_sync(0xffffffffu, n_left);
+                if (lane == 0) {
+                    if (warp == 0) atomicAdd(&dl[0], 1u);
+                    atomicAdd(&dl[1], (unsigned)n_live);
+                    if (n_miss) atomicAdd(&dl[2], (unsigned)n_miss);
+                    if (n_left) { atomicAdd(&dl[3], (unsigned)n_left); atomicAdd(&s->nleft, n_left); }
                 }
-                if (!br.done && final_level) to_sparse(j);
             }
-        }
-        if (warp < 4) {
-            n_live = __reduce_add_sync(0xffffffffu, n_live);
-            n_miss = __reduce_add_sync(0xffffffffu, n_miss);
-            n_left = __reduce_add_sync(0xffffffffu, n_left);
-            if (lane == 0) {
-                if (warp == 0) atomicAdd(&dbg[0], 1u);
-                atomicAdd(&dbg[1], (unsigned)n_live);
-                if (n_miss) atomicAdd(&dbg[2], (unsigned)n_miss);
-                if (n_left) atomicAdd(&dbg[3], (unsigned)n_left);
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_CONS) : "memory");
+            // sweep again only when enough lines are still live to pay for it (short lines start from the whole item range and
+            // need it); otherwise, and after the last level, the sparse refinement takes them as they are
+            const int left = s->nleft;
+            const bool again = level + 1 < LEVELS && left >= DENSE2_MIN_LIVE;
+            valid = valid && sh_a[j] >= 0;                     // (all four parts of a line read what its scanning thread wrote)
+            if (!again) {
+                if (valid && warp < 4) to_sparse(j);
+                if (tid == 0 && level + 1 < LEVELS) { s->go = 0; mbar_arrive(&s->lvl); }
+                break;
             }
+            for (int i = tid; i < (NBIN + 2) * 128; i += TC_CONS) hist[i] = 0u;
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_CONS) : "memory");
+            if (tid == 0) { s->nleft = 0; s->go = 1; mbar_arrive(&s->lvl); }
         }
     }
     tc_end(tmem);
@@ -393,7 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_emit_kernel(TrackSet ts, con
         uint32_t sp = stage0;                                  // next free staging entry of this lane (256 B apart)
         for (int b = 0; b < nblocks; ++b) {
             if (lane < 2 && b + 1 < nblocks) tc_prefetch_l1(rowpack + (b + 1) * TC_N + part * 16 + 8 * lane);   // next block's 16 rows (256 B)
-            tc_consume_block(s, tmem, b, warp, [&](int r0, const int (&v0)[16], const int (&v1)[16], const int (&v2)[16]) {
+            tc_consume_block(s, tmem, b, b, warp, [&](int r0, const int (&v0)[16], const int (&v1)[16], const int (&v2)[16]) {
                 const unsigned rec0 = (unsigned)r0 | jrec;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {

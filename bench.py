@@ -15,7 +15,7 @@ Output: ONE JSON line on rank 0 (contract in the task statement), with
   e2e          the same metric through the product path at every N: all_pairwise_distributed(Serra09) over the
                WHOLE C3 pair list (strong scaling): host pair tiles in, host score tiles out, NCCL gather of the
                score slices at N > 1, N x N matrix assembled and symmetrised; rank-0 tail timed separately
-  roofline     dominant kernel (fast_emit_kernel) against measured HBM bandwidth (contract view) and, in
+  roofline     dominant kernel (the emit sweep: tc_emit_kernel) against measured HBM bandwidth (contract view) and, in
                `roofline.binding`, against the instruction-issue roofline that binds it; DRAM traffic and
                lane-instructions per cell come from the committed ncu capture of this build
                (profiles/k2_constants.json); `roofline_alu` keeps the per-stage / per-kernel breakdown
@@ -43,7 +43,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Per-pair constants of the dominant kernel (fast_emit_kernel) measured by the committed `ncu --set full` capture of
+# Per-pair constants of the dominant kernel (the emit sweep) measured by the committed `ncu --set full` capture of
 # THIS build: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) and executed warp instructions
 # (smsp__inst_executed.sum) of one launch divided by its pairs.  profiles/make_constants.py writes the file from the
 # .ncu-rep kept beside it; it records the git hash it was taken at.
@@ -403,7 +403,7 @@ def main():
             pass
     alg.cleanup_memmap()
 
-    # ---- roofline of the dominant kernel (fast_emit_kernel, the sweep that writes the bit-packed CRP) -------------
+    # ---- roofline of the dominant kernel (the emit sweep, which writes the bit-packed CRP) ---------------------------
     k2_ms = stage["k2_crp"]
     k3_ms = stage["k3_dp"]
     emit_ms = stage.get("k2_emit", 0.0)
@@ -421,8 +421,15 @@ def main():
     lane_inst = ce.get("lane_inst_per_cell")
     binding = None
     if emit_s > 0:
-        binding = {"kind": "instruction issue (the roofline that binds: K = 12 contractions + integer classification, "
-                           "no float CSM in HBM)",
+        # tensor view of the same launch: 30 tcgen05.mma (M 128 x N 64 x K 32 bytes, u8 x u8 -> s32) per block of 128 x 64 cells
+        int8_ops_per_cell = 30 * 2 * 32
+        int8_peak = 4.5e15                                       # nominal dense int8 (B200_PROFILING.md has no measured int8 figure)
+        binding = {"kind": "instruction issue of the consumer warps (per cell: item from three TMEM accumulators, two zone "
+                           "tests, one ballot; the items themselves come from the tensor cores: `tensor` view)",
+                   "tensor": {"int8_ops_per_cell": int8_ops_per_cell, "achieved_tops": int8_ops_per_cell * cells / emit_s / 1e12,
+                              "peak_tops": int8_peak / 1e12, "frac": int8_ops_per_cell * cells / emit_s / int8_peak,
+                              "peak_kind": "nominal dense int8; an N = 64 MMA takes ~51 cycles against a 32-cycle pipe floor "
+                                           "(profiles/r2_umma_probe.md), so ~0.6 of it is reachable at this tile shape"},
                    "achieved_lane_inst_per_s": (lane_inst * cells / emit_s) if lane_inst else None,
                    "peak_lane_inst_per_s": issue_peak,
                    "frac": (lane_inst * cells / emit_s / issue_peak) if lane_inst else None,
@@ -431,7 +438,7 @@ def main():
                             "peak_tflops": fp32_peak / 1e12, "frac": 30 * cells / emit_s / fp32_peak,
                             "peak_kind": "nominal: 148 SMs x 128 lanes x 2 flop at the sampled SM clock (no measured FP32 peak)"},
                    "constants_from": consts.get("source"), "constants_git": consts.get("git")}
-    roofline = {"bound": "hbm", "kernel": "fast_emit_kernel<4> (K2 emit sweep)", "achieved": ach_gbs, "peak": hbm_peak,
+    roofline = {"bound": "hbm", "kernel": ce.get("kernel", "tc_emit_kernel") + " (K2 emit sweep)", "achieved": ach_gbs, "peak": hbm_peak,
                 "unit": "GB/s", "frac": (ach_gbs / hbm_peak) if ach_gbs else None,
                 "traffic": traffic,
                 "traffic_source": consts.get("source"),
@@ -440,8 +447,7 @@ def main():
                 "launches": emit_launches, "ms_per_launch": emit_ms / emit_launches,
                 "k2_stage_ms_per_step": k2_ms / args.steps, "emit_share_of_step": emit_ms / ms,
                 "binding": binding,
-                "note": "the kernel is instruction-issue bound by design (no float CSM in HBM), so the HBM fraction is small; "
-                        "`binding` is the roofline that binds"}
+                "note": "no float CSM ever reaches HBM, so the HBM fraction is small by design; `binding` is the roofline that binds"}
     roofline_alu = {"k2_cells_per_s": cells / (k2_ms / 1e3) if k2_ms > 0 else None,
                     "k3_cells_per_s": cells / (k3_ms / 1e3) if k3_ms > 0 else None,
                     "issue_peak_lane_ops_per_s": issue_peak,

@@ -31,8 +31,8 @@ out = {"git": subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_ou
 for r in data:
     name = r[idx["Kernel Name"]]
     import re
-    mh = re.search(r"fast_hist_kernel<[^,>]*4[^,>]*,\s*[^,>]*([01])\)?>", name)
-    key = "emit" if "fast_emit_kernel" in name else ("hist_col" if mh.group(1) == "0" else "hist_row") if mh else None
+    mh = re.search(r"fast_hist_kernel<[^,>]*4[^,>]*,\s*[^,>]*([01])\)?>", name) or re.search(r"tc_hist_kernel<[^>]*([01])\)?>", name)
+    key = "emit" if ("fast_emit_kernel" in name or "tc_emit_kernel" in name) else ("hist_col" if mh.group(1) == "0" else "hist_row") if mh else None
     if key is None or key in out:
         continue
     winst = val(r, "smsp__inst_executed.sum")
@@ -43,6 +43,7 @@ for r in data:
                 "dram_read_bytes_per_pair": val(r, "dram__bytes_read.sum") / pairs,
                 "dram_write_bytes_per_pair": val(r, "dram__bytes_write.sum") / pairs,
                 "issue_active_pct": float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+                "kernel": re.sub(r"\(.*", "", name).replace("void ", "").replace("<unnamed>::", ""),
                 "registers": int(float(r[idx["launch__registers_per_thread"]]))}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "k2_constants.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))

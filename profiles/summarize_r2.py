@@ -18,6 +18,9 @@ KEYS = [("gpu__time_duration.sum", "duration"), ("launch__registers_per_thread",
         ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
         ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 LSU wavefronts %"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active (realtime) %"),
+        ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor memory cycles active %"),
+        ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "TMEM instruction pipe %"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
         ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
         ("smsp__inst_executed.sum", "warp instructions"),
@@ -105,8 +108,8 @@ md = ["# ncu summary — round 2, final build (captured at git %s)" % git, "",
       "## `--set full` capture of the sweep kernels (`%s`; `tools/k2_time.py --pairs 2048`: one launch = 2048 C3-shaped pairs, 8.15e9 cells)" % rep_sweeps,
       "", raw_table(rep_sweeps), "",
       "Per-pair constants derived from this report: `profiles/k2_constants.json` (`profiles/make_constants.py`).", "",
-      "### Where the emit sweep's instructions and stalls go (source page, per opcode)", "", opcode_table(rep_sweeps, "fast_emit_kernel"), "",
-      "### The same for the column histogram sweep", "", opcode_table(rep_sweeps, "fast_hist_kernel"), "",
+      "### Where the emit sweep's instructions and stalls go (source page, per opcode)", "", opcode_table(rep_sweeps, "tc_emit_kernel|fast_emit_kernel"), "",
+      "### The same for the column histogram sweep", "", opcode_table(rep_sweeps, "tc_hist_kernel|fast_hist_kernel"), "",
       "## `--set full` capture of the other K2 kernels and K3 (same command)", "", raw_table(rep_small, 0.05), ""]
 open("profiles/r2_k2.md", "w").write("\n".join(md))
 print("wrote profiles/r2_k2.md")
