@@ -4,6 +4,7 @@
 //   K1 oti_kernel over all pairs -> pairs are processed in fixed-pitch chunks ("slots"):
 //   K2 (fast sweep path, exact fallback) -> bit-packed CRP per slot -> K3 DP -> scores[k].
 // Nothing here computes on the CPU: without a usable device every call fails with ACOSS_E_CUDA.
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges around stages / K2 kernels (visible to nsys / ncu --nvtx)
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -86,14 +87,19 @@ static cudaEvent_t get_event(acoss_ctx *c) {
     }
     return c->ev_pool[c->ev_used++];
 }
-struct StageTimer {     // records [a, b] around a pipeline stage when profiling is on
-    acoss_ctx *c; int stage; cudaEvent_t a = nullptr;
+static const char *const STAGE_NAMES[9] = {"acoss/K1 oti", "acoss/K2 crp", "acoss/K3 dp", "acoss/K2 emit", "acoss/EF csm", "acoss/EF knn",
+                                           "acoss/EF sw", "acoss/EF radii", "acoss/EF fuse"};
+struct StageTimer {     // NVTX range around a pipeline stage (host side: the enqueue); CUDA events [a, b] when profiling is on
+    acoss_ctx *c; int stage; cudaEvent_t a = nullptr; bool open = true;
     StageTimer(acoss_ctx *c_, int s) : c(c_), stage(s) {
+        nvtxRangePushA(STAGE_NAMES[s < 9 ? s : 1]);
         if (c->profiling) { a = get_event(c); cudaEventRecord(a, c->stream); }
     }
     void stop() {
         if (c->profiling && a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({stage, a, b}); a = nullptr; }
+        if (open) { nvtxRangePop(); open = false; }
     }
+    ~StageTimer() { if (open) nvtxRangePop(); }
 };
 struct CtxKernelTimer : KernelTimer {     // K2 per-kernel spans -> stage_ms[16 + id]; the emit kernel also feeds stage 3
     acoss_ctx *c; cudaEvent_t a[K2K_COUNT];

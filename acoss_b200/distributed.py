@@ -133,16 +133,31 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None, fill_on=None, c
     load, save = _tile_store(checkpoint_dir, rank, world, len(pairs), tile, bounds)
     t1 = time.perf_counter()
     parts, resumed = [], 0
-    for t, k in enumerate(range(0, len(mine), tile)):
-        p = mine[k:k + tile]
-        got = load(t, len(p)) if load else None
-        if got is None:
-            got = score_tile(p)
-            if save:
-                save(t, got)
-        else:
-            resumed += 1
-        parts.append(got)
+    failure = None
+    try:
+        for t, k in enumerate(range(0, len(mine), tile)):
+            p = mine[k:k + tile]
+            got = load(t, len(p)) if load else None
+            if got is None:
+                got = score_tile(p)
+                if save:
+                    save(t, got)
+            else:
+                resumed += 1
+            parts.append(got)
+    except Exception as e:                                  # noqa: BLE001 - reported to every rank below
+        failure = e
+    # A rank whose scoring failed must not leave the others waiting in the gather: agree on the outcome first (one
+    # tiny all_reduce), then every rank raises - the launcher sees non-zero exit codes instead of a hang.
+    if world > 1:
+        backend0 = dist.get_backend()
+        fdev = torch.device("cuda", int(getattr(alg, "device", 0))) if backend0 == "nccl" else torch.device("cpu")
+        flag = torch.tensor([0 if failure is None else 1], dtype=torch.int32, device=fdev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) and failure is None:
+            raise RuntimeError("all_pairwise_distributed: scoring failed on another rank (rank %d had finished its shard)" % rank)
+    if failure is not None:
+        raise RuntimeError("all_pairwise_distributed: scoring failed on rank %d: %s" % (rank, failure)) from failure
     local = np.concatenate(parts, axis=-1) if parts else np.zeros(0, np.float32)
     t2 = time.perf_counter()
     rows = 1 if local.ndim == 1 else local.shape[0]

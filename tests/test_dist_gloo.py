@@ -213,6 +213,53 @@ def test_distributed_all_pairwise_gloo(tmp_path, world):
         assert bounds[0] == 0 and bounds[-1] == n * (n - 1) // 2 and (np.diff(bounds) > 0).all()
 
 
+def _worker_fail(rank, world, port, tmp, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    os.chdir(tmp)
+    import torch.distributed as dist
+    from acoss_b200.distributed import all_pairwise_distributed
+    from acoss_b200.serra09 import Serra09
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    feats = [dict(hpcp=rng.random((int(n), 12)).astype(np.float32), label=str(i // 3))
+             for i, n in enumerate(rng.integers(20, 200, size=17))]
+    alg = Serra09(None, None, features=feats, downsample_fac=1, shortname="f%d" % rank, cachedir="cachef%d" % rank)
+
+    def score(pairs):
+        if rank == 1:
+            raise RuntimeError("device lost")              # what an ACOSS_E_CUDA return code turns into
+        return _fake_score(pairs)
+
+    try:
+        all_pairwise_distributed(alg, symmetric=True, score_fn=score)
+        q.put((rank, "ok"))
+    except RuntimeError as e:
+        q.put((rank, str(e)))
+        dist.destroy_process_group()
+        sys.exit(3)
+    dist.destroy_process_group()
+
+
+def test_distributed_rank_failure_surfaces_everywhere(tmp_path):
+    """A scoring failure on one rank raises on EVERY rank before the gather ('rank-failure surfaces as
+    non-zero rc'): no rank hangs in the collective, every process exits non-zero."""
+    import multiprocessing as mp
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_fail, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    msgs = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 3
+    assert "failed on rank 1" in msgs[1] and "device lost" in msgs[1]
+    assert "another rank" in msgs[0]
+
+
 def test_shard_bounds_balance():
     from acoss_b200.distributed import shard_bounds
     rng = np.random.default_rng(0)
