@@ -131,6 +131,14 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None, fill_on=None, c
         eng = alg.engine()
         score_tile = lambda p: eng.score_pairs(p.astype(np.int32), alg.params())
     load, save = _tile_store(checkpoint_dir, rank, world, len(pairs), tile, bounds)
+    backend = dist.get_backend() if dist.is_initialized() else "none"
+    # staging device: the plugin's own device (alg.device), not whatever torch's current device happens to be —
+    # with one process per GPU every rank must stage on ITS GPU or NCCL deadlocks
+    if backend == "nccl":
+        dev = torch.device("cuda", int(getattr(alg, "device", torch.cuda.current_device())))
+        torch.cuda.set_device(dev)
+    else:
+        dev = torch.device("cpu")
     t1 = time.perf_counter()
     parts, resumed = [], 0
     failure = None
@@ -150,9 +158,7 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None, fill_on=None, c
     # A rank whose scoring failed must not leave the others waiting in the gather: agree on the outcome first (one
     # tiny all_reduce), then every rank raises - the launcher sees non-zero exit codes instead of a hang.
     if world > 1:
-        backend0 = dist.get_backend()
-        fdev = torch.device("cuda", int(getattr(alg, "device", 0))) if backend0 == "nccl" else torch.device("cpu")
-        flag = torch.tensor([0 if failure is None else 1], dtype=torch.int32, device=fdev)
+        flag = torch.tensor([0 if failure is None else 1], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
         if int(flag.item()) and failure is None:
             raise RuntimeError("all_pairwise_distributed: scoring failed on another rank (rank %d had finished its shard)" % rank)
@@ -163,14 +169,6 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None, fill_on=None, c
     rows = 1 if local.ndim == 1 else local.shape[0]
     if rows not in (1, len(keys)):
         raise ValueError("score rows (%d) do not match the score types %r" % (rows, keys))
-    backend = dist.get_backend() if dist.is_initialized() else "none"
-    # staging device: the plugin's own device (alg.device), not whatever torch's current device happens to be —
-    # with one process per GPU every rank must stage on ITS GPU or NCCL deadlocks
-    if backend == "nccl":
-        dev = torch.device("cuda", int(getattr(alg, "device", torch.cuda.current_device())))
-        torch.cuda.set_device(dev)
-    else:
-        dev = torch.device("cpu")
     # one gather for all score rows: rank r contributes rows x (bounds[r+1] - bounds[r]) floats, row-major
     flat = np.ascontiguousarray(local.reshape(rows, -1)).ravel()
     full = gather_scores(torch.from_numpy(flat).to(dev), bounds * rows, rank, world)
