@@ -57,3 +57,31 @@ def test_sass_is_sm100_with_dpx():
         out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100" in out
     assert "VIMNMX3.S16x2" in out and "VIADDMNMX.S16x2.RELU" in out
+
+
+def test_sass_has_tcgen05_tensor_sweeps():
+    """The K2 tensor sweeps are compiled as tcgen05 code: integer MMAs issued from tensor / shared memory (UTCIMMA), TMEM
+    loads and stores (LDTM / STTM), tcgen05.commit (UTCBAR), TMEM allocation (UTCATOMSWS), TMA bulk copies (UBLKCP); the
+    sparse level's limb products are dp4a (IDP.4A); the short-line sweeps keep the packed FFMA2."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            funcs[cur] = []
+        elif cur:
+            funcs[cur].append(line)
+    def body(tag):
+        return "\n".join("\n".join(v) for k, v in funcs.items() if tag in k)
+    for tag in ("tc_hist_kernel", "tc_emit_kernel"):
+        b = body(tag)
+        assert b.count("UTCIMMA") == 30 * (2 if tag == "tc_hist_kernel" else 1), tag      # 30 MMAs per block (hist: two orientations)
+        for op in ("LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "UBLKCP", "SYNCS"):
+            assert op in b, (tag, op)
+    assert "IDP.4A" in body("tc_sparse_kernel")
+    assert "FFMA2" in body("fast_emit_kernel")
