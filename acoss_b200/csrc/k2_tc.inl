@@ -279,8 +279,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
         if (pos < gcap) glive[1 + pos] = ((uint32_t)slot << 16) | ((uint32_t)side << 15) | (uint32_t)line;
         else atomicOr(&status[k], PAIR_ST_FALLBACK | 8u);     // reason 8: too many crowded lines in this call
     };
+#ifdef TC_PHASES
+    const long long T0 = clock64();
+    long long Tf = 0, T3 = 0, T4 = 0;
+#endif
     for (int i = tid; i < (NBIN + 2) * 128; i += TC_THREADS) hist[i] = 0u;
     const uint32_t tmem = tc_begin(s);
+#ifdef TC_PHASES
+    const long long T1 = clock64();
+#endif
     const int nblocks = (Mxs + TC_N - 1) / TC_N;
     constexpr int LEVELS = 2;                                 // dense levels a CTA may run back to back (operand tiles stay in TMEM)
     if (!cons) {
@@ -312,7 +319,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
                         }
                     }
                 });
+#ifdef TC_PHASES
+                if (b == 0 && level == 0) Tf = clock64();
+#endif
             }
+#ifdef TC_PHASES
+            if (level == 0) T3 = clock64();
+#endif
             asm volatile("bar.sync 1, %0;" ::"n"(TC_CONS) : "memory");
             // one thread per line scans (all parts counted into one histogram)
             const bool scan = valid && warp < 4;
@@ -350,6 +363,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
             const int left = s->nleft;
             const bool again = level + 1 < LEVELS && left >= DENSE2_MIN_LIVE;
             valid = valid && sh_a[j] >= 0;                     // (all four parts of a line read what its scanning thread wrote)
+#ifdef TC_PHASES
+            if (level == 0) T4 = clock64();
+#endif
             if (!again) {
                 if (valid && warp < 4) to_sparse(j);
                 if (tid == 0 && level + 1 < LEVELS) { s->go = 0; mbar_arrive(&s->lvl); }
@@ -361,6 +377,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_hist_kernel(TrackSet ts, con
         }
     }
     tc_end(tmem);
+#ifdef TC_PHASES
+    if (tid == 0 && ORIENT == 0) {                              // (orientation 1's counter block overlaps other counters)
+        const long long T5 = clock64();
+        atomicAdd(&dbg[20], (unsigned)((T1 - T0) >> 6)); atomicAdd(&dbg[21], (unsigned)((Tf - T1) >> 6));
+        atomicAdd(&dbg[22], (unsigned)((T3 - Tf) >> 6)); atomicAdd(&dbg[23], (unsigned)((T4 - T3) >> 6));
+        atomicAdd(&dbg[26], (unsigned)((T5 - T4) >> 6)); atomicAdd(&dbg[27], 1u);
+        atomicAdd(&dbg[28], (unsigned)nblocks);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
