@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["shard_bounds", "gather_scores", "all_pairwise_distributed"]
+__all__ = ["shard_bounds", "triangle_shard", "gather_scores", "all_pairwise_distributed"]
 
 
 def shard_bounds(weights, world: int) -> np.ndarray:
@@ -27,6 +27,52 @@ def shard_bounds(weights, world: int) -> np.ndarray:
     cuts = np.searchsorted(c, targets, side="left")
     b = np.concatenate([[0], cuts, [n]]).astype(np.int64)
     return np.maximum.accumulate(b)
+
+
+def triangle_shard(a, world: int, rank: int):
+    """The same split for the upper-triangle pair list (i < j, row-major = itertools.combinations order) with product
+    weights w_ij = a_i a_j, WITHOUT building the list: at 15 000 tracks the list has 1.1e8 pairs and every rank would
+    spend seconds and gigabytes on pairs it never scores.  Row i holds N-1-i pairs of weight a_i * (a_{i+1} + ...): the
+    cut points are located by row, then inside the row.  Returns (bounds[0..world], this rank's pairs as (n, 2) int64);
+    the bounds equal shard_bounds(weights of the full list, world)."""
+    a = np.asarray(a, dtype=np.float64)
+    n = len(a)
+    cnt = np.arange(n - 1, -1, -1, dtype=np.int64)                     # pairs per row
+    start = np.concatenate([[0], np.cumsum(cnt)])                      # first pair index of each row
+    total_pairs = int(start[-1])
+    suffix = np.concatenate([np.cumsum(a[::-1])[::-1][1:], [0.0]])     # a_{i+1} + ... + a_{n-1}
+    roww = a * suffix
+    crow = np.concatenate([[0.0], np.cumsum(roww)])                    # weight before each row
+
+    def cum_at(k):                                                     # weight of the first k pairs, as np.cumsum accumulates it
+        i = int(np.searchsorted(start, k, side="right") - 1)
+        i = min(i, n - 1)
+        return i, k - int(start[i])
+
+    if world <= 1 or total_pairs == 0:
+        bounds = np.array([0, total_pairs] + [total_pairs] * max(0, world - 1), dtype=np.int64)[:world + 1]
+    else:
+        targets = crow[-1] * np.arange(1, world) / world
+        cuts = []
+        for t in targets:
+            i = int(np.searchsorted(crow, t, side="right") - 1)       # row holding the cut
+            i = max(0, min(i, n - 2))
+            inrow = crow[i] + a[i] * np.concatenate([[0.0], np.cumsum(a[i + 1:])])
+            off = int(np.searchsorted(inrow, t, side="left"))
+            cuts.append(int(start[i]) + min(off, int(cnt[i])))
+        bounds = np.maximum.accumulate(np.array([0] + cuts + [total_pairs], dtype=np.int64))
+    k0, k1 = int(bounds[rank]), int(bounds[rank + 1])
+    if k1 <= k0:
+        return bounds, np.zeros((0, 2), dtype=np.int64)
+    (i0, o0), (i1, o1) = cum_at(k0), cum_at(k1 - 1)
+    rows = np.arange(i0, i1 + 1, dtype=np.int64)
+    first = np.where(rows == i0, o0, 0)
+    last = np.where(rows == i1, o1 + 1, cnt[rows])
+    lens = last - first
+    ii = np.repeat(rows, lens)
+    within = np.arange(lens.sum(), dtype=np.int64) - np.repeat(np.cumsum(lens) - lens, lens)
+    jj = ii + 1 + np.repeat(first, lens) + within
+    return bounds, np.stack([ii, jj], axis=1)
 
 
 def gather_scores(local_scores, bounds, rank: int, world: int, device=None):
@@ -111,16 +157,25 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None, fill_on=None, c
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     t0 = time.perf_counter()
-    pairs = alg._pair_array(symmetric)
-    if hasattr(alg, "pair_weights"):
-        cells = np.asarray(alg.pair_weights(pairs), dtype=np.float64)
-    else:
+    pairs = None                                            # the full pair list: built lazily (only the assembling rank needs it)
+    if symmetric and not hasattr(alg, "pair_weights"):
+        # Serra09-style plugin, upper triangle: product weights -> the shard is computed without the 1e8-pair list
         lens = np.array([alg.load_features(i).shape[0] for i in range(alg.N)], dtype=np.int64)
         incr = int(alg.m) * int(alg.tau)
-        cells = (lens[pairs[:, 0]] - incr) * (lens[pairs[:, 1]] - incr)
-    bounds = shard_bounds(cells, world)
-    del cells
-    mine = pairs[bounds[rank]:bounds[rank + 1]]
+        bounds, mine = triangle_shard(lens - incr, world, rank)
+        n_pairs = int(bounds[-1])
+    else:
+        pairs = alg._pair_array(symmetric)
+        if hasattr(alg, "pair_weights"):
+            cells = np.asarray(alg.pair_weights(pairs), dtype=np.float64)
+        else:
+            lens = np.array([alg.load_features(i).shape[0] for i in range(alg.N)], dtype=np.int64)
+            incr = int(alg.m) * int(alg.tau)
+            cells = (lens[pairs[:, 0]] - incr) * (lens[pairs[:, 1]] - incr)
+        bounds = shard_bounds(cells, world)
+        del cells
+        mine = pairs[bounds[rank]:bounds[rank + 1]]
+        n_pairs = len(pairs)
     keys = list(alg.Ds.keys())
     tile = int(getattr(alg, "tile_pairs", 1 << 16))
     if score_fn is not None:
@@ -130,7 +185,7 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None, fill_on=None, c
     else:
         eng = alg.engine()
         score_tile = lambda p: eng.score_pairs(p.astype(np.int32), alg.params())
-    load, save = _tile_store(checkpoint_dir, rank, world, len(pairs), tile, bounds)
+    load, save = _tile_store(checkpoint_dir, rank, world, n_pairs, tile, bounds)
     backend = dist.get_backend() if dist.is_initialized() else "none"
     # staging device: the plugin's own device (alg.device), not whatever torch's current device happens to be —
     # with one process per GPU every rank must stage on ITS GPU or NCCL deadlocks
@@ -176,6 +231,8 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None, fill_on=None, c
         torch.cuda.synchronize(dev)
     t3 = time.perf_counter()
     if fill_on is None or fill_on == rank:
+        if pairs is None:
+            pairs = alg._pair_array(symmetric)
         fill_score_matrices(alg, pairs, full, bounds, rows, keys, symmetric, world)
     t4 = time.perf_counter()
     if timings is not None:

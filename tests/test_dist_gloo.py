@@ -260,6 +260,23 @@ def test_distributed_rank_failure_surfaces_everywhere(tmp_path):
     assert "another rank" in msgs[0]
 
 
+def test_triangle_shard_equals_list_split():
+    """The list-free split of the upper triangle gives the bounds and the slices of shard_bounds over the full pair list."""
+    from acoss_b200.distributed import shard_bounds, triangle_shard
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 5, 17, 160, 700):
+        a = rng.integers(1, 2500, size=n).astype(np.int64)
+        i, j = np.triu_indices(n, 1)
+        pairs = np.stack([i, j], 1)
+        w = (a[i] * a[j]).astype(np.float64)
+        for world in (1, 2, 3, 8):
+            b0 = shard_bounds(w, world)
+            for r in range(world):
+                b, mine = triangle_shard(a, world, r)
+                assert np.array_equal(b, b0)
+                assert np.array_equal(mine, pairs[b0[r]:b0[r + 1]])
+
+
 def test_shard_bounds_balance():
     from acoss_b200.distributed import shard_bounds
     rng = np.random.default_rng(0)
