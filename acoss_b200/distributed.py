@@ -231,8 +231,6 @@ def all_pairwise_distributed(alg, symmetric=True, score_fn=None, fill_on=None, c
         torch.cuda.synchronize(dev)
     t3 = time.perf_counter()
     if fill_on is None or fill_on == rank:
-        if pairs is None:
-            pairs = alg._pair_array(symmetric)
         fill_score_matrices(alg, pairs, full, bounds, rows, keys, symmetric, world)
     t4 = time.perf_counter()
     if timings is not None:
@@ -247,19 +245,23 @@ def fill_score_matrices(alg, pairs, full, bounds, rows, keys, symmetric, world):
     copy), in a private ndarray otherwise — and then written to alg.Ds[key] by a plain, idempotent assignment.
     Ranks of one box that were constructed with the same cache prefix map the same memmap file: an in-place
     `Ds += Ds.T` on the shared file would symmetrise twice (scores doubled); a plain assignment of the finished
-    matrix cannot."""
+    matrix cannot.  `pairs=None`: the full upper triangle in combinations order (indices generated on the staging device)."""
     import torch
     N = int(alg.N)
+    n_pairs = len(pairs) if pairs is not None else N * (N - 1) // 2
     # rank r's slice holds its rows back to back (row-major rows x n_r): un-interleave into (rows, n_pairs)
     if rows == 1:
         per_key = full.reshape(1, -1)
     else:
-        per_key = torch.empty((rows, len(pairs)), dtype=torch.float32, device=full.device)
+        per_key = torch.empty((rows, n_pairs), dtype=torch.float32, device=full.device)
         for r in range(world):
             a, b = int(bounds[r]), int(bounds[r + 1])
             per_key[:, a:b] = full[a * rows:b * rows].reshape(rows, b - a)
-    pi = torch.from_numpy(np.ascontiguousarray(pairs[:, 0]).astype(np.int64)).to(full.device)
-    pj = torch.from_numpy(np.ascontiguousarray(pairs[:, 1]).astype(np.int64)).to(full.device)
+    if pairs is None:
+        pi, pj = torch.triu_indices(N, N, offset=1, device=full.device)      # row-major: itertools.combinations order
+    else:
+        pi = torch.from_numpy(np.ascontiguousarray(pairs[:, 0]).astype(np.int64)).to(full.device)
+        pj = torch.from_numpy(np.ascontiguousarray(pairs[:, 1]).astype(np.int64)).to(full.device)
     for k, key in enumerate(keys):
         D = torch.zeros((N, N), dtype=torch.float32, device=full.device)
         D.index_put_((pi, pj), per_key[k if rows > 1 else 0])
