@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["api.cu", "k0_onramp.cu", "k1_oti.cu", "k2_exact.cu", "k2_fast.cu", "k3_dp.cu", "k4_knn.cu", "k5_earlyfusion.cu"]
-HEADERS = ["common.cuh", "k2_fast.cuh", "../../include/acoss_b200.h"]
+HEADERS = ["common.cuh", "k2_fast.cuh", "k2_tc.inl", "../../include/acoss_b200.h"]
 OUT = os.path.join(HERE, "libacoss_b200.so")
 import os as _os
 EXTRA = _os.environ.get("ACOSS_NVCC_EXTRA", "").split()

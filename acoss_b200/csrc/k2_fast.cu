@@ -3,7 +3,12 @@
 //
 // Replaces essentia ChromaCrossSimilarity (call site
 // /root/reference/acoss/algorithms/rqa_serra09.py:60-66).  Results are bit-identical to the
-// reference-order arithmetic of k2_exact.cu; the structure is:
+// reference-order arithmetic of k2_exact.cu.  The three sweeps over the cell matrix (row thresholds, column
+// thresholds, emit) exist twice and launch_k2_fast picks per call: on the tensor cores (k2_tc.inl: the stacked
+// 108-term inner product as an exact integer GEMM, tcgen05.mma kind::i8 over byte-limb planes, items read from
+// tensor memory) for lines of K2_TC_MIN_WINDOWS windows or more, and as FFMA2 chains on the CUDA cores (this file)
+// for short lines and for features that cannot be quantised inside the error budget.  Everything around the sweeps
+// (prep, sampler, selection, candidate lists, exact thresholds, bit patch) is shared.  Structure of the FFMA2 form:
 //
 //  * The stacked squared distance is a 9-tap diagonal sum of the frame-level dot product
 //    e[a][c] = <x_a, y_c> (12 FMAs):  item(i,j) = aa_i + bb_j - 2 * sum_t e[i+t][j+t].
