@@ -12,15 +12,20 @@
 //     bytes, row r / tap t is frame r + t, so core matrix (rows r0 .. r0+7, tap t) IS the 128 contiguous bytes at
 //     frame r0 + t of the plane: leading byte offset 16 (next tap), stride byte offset 128 (next 8 rows).  One
 //     MMA covers two taps; the ninth tap pairs with a block of zeros on the streamed side.  30 MMAs per block;
-//   * consumer threads read their owned window's 64 items from TMEM (tcgen05.ld 32x32b: TMEM lane = owned window,
+//   * one CTA per SM = 128 owned windows x all streamed windows: the owned operand (15 tiles of 128 rows x 32 bytes) is
+//     written once into tensor memory and every MMA takes A from there (TS form); two accumulator buffers, so the
+//     tensor cores fill block b + 1 while the consumers read block b; warp roles: TMA loader, two MMA issuers, sixteen
+//     consumer warps;
+//   * consumer threads read their owned window's items from TMEM (tcgen05.ld 32x32b: TMEM lane = owned window,
 //     column = streamed window) and bin / classify them: no dot products, no sliding sums, no shuffles on the
 //     CUDA cores.
-// T = (acc0 << s0) + ((acc1 * 256 + acc2) >> s2) is 2 <X, Y> in the fixed-point unit of the path (shifts from q_exp and
+// T = acc0 * 2^e0 + ((acc1 * 256 + acc2) >> (16 - e0)) is 2 <X, Y> in the fixed-point unit of the path (e0 = 56 - 2 q_exp -
 // fx_exp); the sparse level evaluates the same integer formula with dp4a, so every kernel sees identical items.
-// Error budget against the exact item: quantisation 216 x_max 2^-(q_exp+1) * 2, dropped limb products
-// 2 * 108 * 255^2 * 2^(9 - 2 q_exp), two floors: 36 units at HPCP scale, inside EPS.
+// Error budget against the exact item, in fixed-point units: quantisation <= 1.4 * 2^(e0/2), dropped limb
+// products <= 0.84 * 2^e0, one floor, the norm roundings and the oracle's float32 roundings (17): 84 at e0 = 6, inside
+// EPS = 128; acoss_set_tracks enables these sweeps only for e0 <= 6.
 
-struct TcShift { int s0, s1, s2; unsigned m0; };   // m0 = 2^s0
+struct TcShift { int s0, s1, s2; unsigned m0; };   // e0, 8 - e0, 16 - e0, 2^e0
 
 constexpr int TC_AF = 144;                          // owned frames held per plane (128 windows + 9 taps, rounded)
 constexpr int TC_ALOAD = 137;                       // owned frames loaded per plane
@@ -57,16 +62,6 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t lbo_bytes) {
 // instruction descriptor: s32 accumulators, u8 x u8, both K-major, M = 128, N = TC_N
 constexpr uint32_t TC_IDESC = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
-        : "memory");
-}
 // A operand from tensor memory (lane = row, 8 columns = the row's 32 bytes)
 __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
