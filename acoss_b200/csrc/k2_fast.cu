@@ -1714,7 +1714,9 @@ int launch_k2_fast(const TrackSet &ts, const int32_t *pairs, const int32_t *oti,
                                                                                       g.words, g.crp_words, status, dbg);
     CUDA_TRY(cudaGetLastError());
     te(K2K_BITS);
-    if (launches) *launches += 17;
+    // kernels launched above: prep, sample, select, sparse, emit, scatter, rank, exact, thr, bits + the histogram sweeps (one
+    // launch per orientation on the tensor cores, two with the FFMA2 sweeps)
+    if (launches) *launches += (no_sample ? 8 : 10) + (use_tc ? 2 : 4);
     return ACOSS_OK;
 }
 
